@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- encrypted 8x8 DCT + quantize throughput (blocks/s), BASELINE.json's metric.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm (CUDA path, C-ABI)
+  python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU arm (oracle op-by-op graph)
+  torchrun ... bench.py --gpus N ...                             # one rank per GPU, weak scaling
+
+A "step" is one pass of the hot path (encrypted_dct + quantize_fhe, fhe_image.h:196-305) over one
+resident chunk of synthetic ciphertext blocks of BASELINE config 2 (server_jpeg DCT+quantize,
+1024x1024 RGB = 49152 blocks, n=4096, k=2, t=2^14).  The 384 GiB image does not fit in HBM, so it
+is streamed as chunks of --blocks blocks (default 8192 = 1/6 of the image, 64 GiB in + 64 GiB
+out); inputs are generated on the device (seeded SplitMix64, uniform residues)
+before the timed region.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RING, T_PLAIN = 4096, 1 << 14
+IMAGE_BLOCKS = 3 * 16384  # 1024x1024 RGB
+METRIC = "encrypted 8x8 DCT+quantize blocks/sec"
+UNIT = "blocks/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(threads, blocks):
+    """Oracle (CPU restatement of the reference's op-by-op graph) on a bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    pkg = importlib.import_module("fully-homomorphic-image-processing_b200")
+    o = oracle_py.Oracle(N_RING, None, T_PLAIN)
+    data = o.fill_uniform(0, 64 * blocks)
+    secs = o.bench_dct_quant(data, blocks, pkg.YQT, threads)
+    return blocks / secs, secs
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU path.  SEAL is absent from /root/reference (empty
+    submodule), so this is the oracle port ("kind": "port"): encrypted_dct + quantize_fhe op by op
+    with the reference's copies, blocks spread over all host threads.  Rank 0 only."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    blocks = max(threads, min(2 * threads, 128))
+    for _ in range(args.warmup):
+        cpu_sample(threads, max(1, threads // 2))
+    t = 0.0
+    for _ in range(args.steps):
+        _, s = cpu_sample(threads, blocks)
+        t += s
+    value = blocks * args.steps / t
+    sample = f"{blocks} blocks/step (64 size-2 cts each, n=4096 k=2), {threads} threads, op-by-op graph"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": "server_jpeg DCT+quantize 1024x1024 RGB, n=4096 k=2 t=2^14 (bounded CPU sample)",
+                   "blocks_per_step": blocks},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--blocks", type=int, default=8192, help="blocks per step per GPU (resident chunk)")
+    ap.add_argument("--e2e-blocks", type=int, default=256, help="blocks per end-to-end step (host buffers)")
+    ap.add_argument("--chunk", type=int, default=0, help="internal chunk blocks (0 = one chunk)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert args.warmup >= 3, "timing rules: at least 3 warm-up steps"
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = importlib.import_module("fully-homomorphic-image-processing_b200")
+    pkg.build()
+
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx = pkg.Context(N_RING, None, T_PLAIN, device=local_rank, stream=stream.cuda_stream)
+    enc = pkg.FractionalEncoder(N_RING, T_PLAIN)
+    plan = pkg.DctPlan(ctx, enc, pkg.YQT)
+    if args.chunk:
+        ctx.set_dct_chunk_blocks(args.chunk)
+
+    # ---- resident inputs: this rank's shard of the (weak-scaled) job --------------------------
+    B = args.blocks
+    words = B * ctx.block_words()
+    d_in = torch.empty(words, dtype=torch.int64, device="cuda")
+    d_out = torch.empty(words, dtype=torch.int64, device="cuda")
+    first_block = rank * B
+    ctx.fill_uniform(d_in.data_ptr(), first_block * 64, B * 64)
+    ctx.sync()
+
+    def step():
+        pkg.encrypted_dct_quantize(ctx, plan, d_in.data_ptr(), d_out.data_ptr(), B)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    # per-kernel times (events between the three kernels), outside the timed region
+    ctx.set_stage_timing(True)
+    stage = [0.0, 0.0, 0.0]
+    for _ in range(3):
+        step()
+        st = ctx.stage_times_ms()
+        stage = [a + b / 3 for a, b in zip(stage, st)]
+    ctx.set_stage_timing(False)
+
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop()
+    launches = ctx.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # edge collective only: checksum of every rank's output
+    cs = ctx.checksum(d_out.data_ptr(), words)
+    cs_t = torch.tensor([cs & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(cs_t, op=dist.ReduceOp.BXOR)
+
+    # ---- end to end through the C-ABI with HOST (pinned) buffers, copies inside the call -------
+    del d_in, d_out
+    torch.cuda.empty_cache()
+    EB = args.e2e_blocks
+    ebytes = EB * ctx.block_words() * 8
+    h_in, h_out = pkg.host_alloc(ebytes), pkg.host_alloc(ebytes)
+    tmp = torch.empty(EB * ctx.block_words(), dtype=torch.int64, device="cuda")
+    ctx.fill_uniform(tmp.data_ptr(), first_block * 64, EB * 64)
+    import ctypes as C
+    pkg._check(pkg.lib().fhe_download(ctx.h, C.c_void_p(h_in), C.c_void_p(tmp.data_ptr()), ebytes))
+    del tmp
+    for _ in range(2):
+        pkg.encrypted_dct_quantize_host(ctx, plan, h_in, h_out, EB)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 6))
+    for _ in range(e2e_steps):
+        pkg.encrypted_dct_quantize_host(ctx, plan, h_in, h_out, EB)
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * EB * e2e_steps / float(te.item())
+    pkg.host_free(h_in); pkg.host_free(h_out)
+
+    # ---- roofline of the dominant kernel (each ciphertext read once + written once)
+    peak, peak_src = measured_peaks()
+    ct_bytes = ctx.ct_bytes(2)
+    launch_bytes = 2 * 64 * ct_bytes * B          # a kernel of the path reads and writes the chunk once
+    names = ["ntt_fwd", "dct_pointwise", "ntt_inv"]
+    dom = max(range(3), key=lambda i: stage[i])
+    achieved = launch_bytes / (stage[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(names[dom])
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": launch_bytes,
+                "stage_ms": dict(zip(names, stage)),
+                "path_achieved": value / world * 2 * 64 * ct_bytes / 1e9,
+                "path_frac": value / world * 2 * 64 * ct_bytes / 1e9 / peak}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        blocks = max(threads, min(4 * threads, 128))
+        v, secs = cpu_sample(threads, blocks)
+        v1, _ = cpu_sample(1, 4)
+        cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{blocks} blocks of the same workload in {secs:.2f} s on {threads} threads "
+                         f"(oracle, op-by-op reference graph); single thread: {v1:.2f} blocks/s",
+               "single_thread_value": v1}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": "server_jpeg DCT+quantize, 1024x1024 RGB (3x16384 blocks), n=4096 k=2 t=2^14, "
+                                   "streamed as HBM-resident chunks",
+                       "blocks_per_step_per_gpu": B, "image_blocks": IMAGE_BLOCKS,
+                       "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"blocks sharded x{world}",
+                       "internal_chunk_blocks": args.chunk},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ebytes, "d2h_bytes_per_step": ebytes,
+                    "blocks_per_step": EB, "steps": e2e_steps},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "output_checksum_xor": hex(int(cs_t.item())),
+        }))
+    plan.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

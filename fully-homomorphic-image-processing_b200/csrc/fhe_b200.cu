@@ -1,0 +1,895 @@
+// fhe_b200.cu -- kernels and C-ABI of libfhe_b200.so (see include/fhe_b200.h).
+//
+// sm_100a only.  No tensor cores: the path is 64-bit integer modular arithmetic on the
+// IMAD/ALU pipes, staged through shared memory, with coalesced HBM access (north_star).
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/fhe_b200.h"
+#include "dct.cuh"
+#include "ntt.cuh"
+#include "ring_host.hpp"
+
+using namespace fhe;
+
+// =============================================================================================
+// device-side context
+// =============================================================================================
+struct RingDev {
+    uint32_t n, logn, k;
+    u64 t, plain_thr, q_mod_t;
+    LimbDev limb[16];
+    u64 delta[16], ratio0[16], ratio1[16];
+    const W2 *tw, *itw;  // [k][n]
+};
+
+// =============================================================================================
+// NTT kernels: one CTA per limb-polynomial, n/E threads (csrc/ntt.cuh)
+// =============================================================================================
+template <int LOGN, int LOGE, class RC, bool OUT_FULL>
+__global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_ntt_fwd(const u64 *in, u64 *out, RingDev R)
+{
+    using S = NttShape<LOGN, LOGE>;
+    static_assert(S::NPASS == 3, "pass chain written for 3 passes");
+    extern __shared__ u64 smem[];
+    const size_t p = blockIdx.x;
+    const int j = (int)(p % R.k), tau = threadIdx.x;
+    const u64 *gin = in + p * S::N;
+    u64 *gout = out + p * S::N;
+    const W2 *tw = R.tw + (size_t)j * S::N;
+    const LimbDev lp = R.limb[j];
+    ntt_fwd_pass<LOGN, LOGE, 0, RC, OUT_FULL>(tau, gin, gout, smem, tw, lp);
+    __syncthreads();
+    ntt_fwd_pass<LOGN, LOGE, 1, RC, OUT_FULL>(tau, gin, gout, smem, tw, lp);
+    __syncthreads();
+    ntt_fwd_pass<LOGN, LOGE, 2, RC, OUT_FULL>(tau, gin, gout, smem, tw, lp);
+}
+
+template <int LOGN, int LOGE, class RC>
+__global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_ntt_inv(const u64 *in, u64 *out, RingDev R)
+{
+    using S = NttShape<LOGN, LOGE>;
+    static_assert(S::NPASS == 3, "pass chain written for 3 passes");
+    extern __shared__ u64 smem[];
+    const size_t p = blockIdx.x;
+    const int j = (int)(p % R.k), tau = threadIdx.x;
+    const u64 *gin = in + p * S::N;
+    u64 *gout = out + p * S::N;
+    const W2 *itw = R.itw + (size_t)j * S::N;
+    const LimbDev lp = R.limb[j];
+    ntt_inv_pass<LOGN, LOGE, 2, RC>(tau, gin, gout, smem, itw, lp);
+    __syncthreads();
+    ntt_inv_pass<LOGN, LOGE, 1, RC>(tau, gin, gout, smem, itw, lp);
+    __syncthreads();
+    ntt_inv_pass<LOGN, LOGE, 0, RC>(tau, gin, gout, smem, itw, lp);
+}
+
+// Evaluator::multiply_plain as ONE kernel per limb-poly: forward NTT (lazy), dyadic product with
+// the pre-transformed plaintext (Shoup), inverse NTT -- the polynomial is read from HBM once and
+// written once; the NTT-domain values never leave the SM.
+template <int LOGN, int LOGE, class RC>
+__global__ void __launch_bounds__(1 << (LOGN - LOGE))
+k_mulplain(const u64 *in, u64 *out, const W2 *__restrict__ table, RingDev R)
+{
+    using S = NttShape<LOGN, LOGE>;
+    static_assert(S::NPASS == 3, "pass chain written for 3 passes");
+    extern __shared__ u64 smem[];
+    const size_t p = blockIdx.x;
+    const int j = (int)(p % R.k), tau = threadIdx.x;
+    const u64 *gin = in + p * S::N;
+    u64 *gout = out + p * S::N;
+    const W2 *tw = R.tw + (size_t)j * S::N, *itw = R.itw + (size_t)j * S::N;
+    const W2 *tab = table + (size_t)j * S::N;
+    const LimbDev lp = R.limb[j];
+    ntt_fwd_pass<LOGN, LOGE, 0, RC, false>(tau, gin, gout, smem, tw, lp);
+    __syncthreads();
+    ntt_fwd_pass<LOGN, LOGE, 1, RC, false>(tau, gin, gout, smem, tw, lp);
+    __syncthreads();
+    u64 v[S::E];
+    ntt_fwd_load<LOGN, LOGE, 2>(v, tau, gin, smem);
+    ntt_fwd_compute<LOGN, LOGE, 2, RC>(v, tau, tw, lp);
+#pragma unroll
+    for (int e = 0; e < S::E; ++e) v[e] = shoup_lazy(v[e], tab[e * S::T + tau], lp.q);
+    ntt_inv_compute<LOGN, LOGE, 2, RC>(v, tau, itw, lp);
+    ntt_inv_store<LOGN, LOGE, 2>(v, tau, gout, smem);
+    __syncthreads();
+    ntt_inv_pass<LOGN, LOGE, 1, RC>(tau, gin, gout, smem, itw, lp);
+    __syncthreads();
+    ntt_inv_pass<LOGN, LOGE, 0, RC>(tau, gin, gout, smem, itw, lp);
+}
+
+// =============================================================================================
+// pointwise DCT (+quantize) kernel (csrc/dct.cuh)
+// =============================================================================================
+// CTA = 8 warps on one (limb, 32-position tile); loops over `upc` consecutive units
+// (unit = one poly of one block: 64 limb-polys, one per ciphertext of the block) so the
+// 12 + 8 Shoup constants a thread needs stay in registers across units.
+__global__ void __launch_bounds__(256, 2)
+k_dct_pointwise(u64 *data, const W2 *__restrict__ ctab, const W2 *__restrict__ stab, RingDev R,
+                unsigned long long nunits, int upc)
+{
+    __shared__ u64 sbuf[2][64 * DCT_TILE];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n = R.n, k = R.k, tiles = n / DCT_TILE;
+    const uint32_t tile = blockIdx.x % tiles, j = (blockIdx.x / tiles) % k;
+    const unsigned long long ug = blockIdx.x / (tiles * k);
+    const size_t pos = (size_t)tile * DCT_TILE + lane;
+    const u64 q = R.limb[j].q;
+    W2 c[DCT_NCONST], s[8];
+#pragma unroll
+    for (int i = 0; i < DCT_NCONST; ++i) c[i] = ctab[((size_t)i * k + j) * n + pos];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s[i] = stab[((size_t)(8 * i + w) * k + j) * n + pos];
+    const size_t ct_stride = (size_t)2 * k * n;
+    for (int it = 0; it < upc; ++it) {
+        const unsigned long long u = ug * upc + it;
+        if (u >= nunits) break;
+        const unsigned long long blk = u >> 1;
+        const uint32_t poly = (uint32_t)(u & 1);
+        u64 *base = data + blk * 64 * ct_stride + ((size_t)poly * k + j) * n + (size_t)tile * DCT_TILE;
+        u64 *sb = sbuf[it & 1];
+        dct_row_phase(w, lane, base, ct_stride, sb, c, q);
+        __syncthreads();
+        dct_col_phase(w, lane, base, ct_stride, sb, c, s, q);
+    }
+}
+
+// =============================================================================================
+// element-wise kernels
+// =============================================================================================
+// flat arrays of limb-polys [..][limb][n]; limb of element i is (i / n) % k
+template <int OP>  // 0 add, 1 sub, 2 negate
+__global__ void k_elementwise(u64 *a, const u64 *b, unsigned long long total, RingDev R)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const u64 q = R.limb[(i >> R.logn) % R.k].q;
+        u64 x = a[i];
+        if (OP == 0) x = addmod(x, b[i], q);
+        else if (OP == 1) x = submod(x, b[i], q);
+        else x = negmod(x, q);
+        a[i] = x;
+    }
+}
+
+// centred lift of plaintexts [count][n] (< t) into [count][k][n]  
+__global__ void k_plain_lift(const u64 *plain, u64 *out, unsigned long long total, RingDev R)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i & (R.n - 1)), j = (uint32_t)((i >> R.logn) % R.k);
+        const unsigned long long pl = (i >> R.logn) / R.k;
+        const u64 m = plain[pl * R.n + c];
+        out[i] = m >= R.plain_thr ? m + (R.limb[j].q - R.t) : m;
+    }
+}
+// Delta-scaling of plaintexts (Encryptor::preencrypt): [count][n] -> [count][k][n]
+__global__ void k_plain_scale(const u64 *plain, u64 *out, unsigned long long total, RingDev R)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i & (R.n - 1)), j = (uint32_t)((i >> R.logn) % R.k);
+        const unsigned long long pl = (i >> R.logn) / R.k;
+        const u64 m = plain[pl * R.n + c];
+        u64 lo = R.delta[j] * m, hi = mulhi_u64(R.delta[j], m);
+        if (m >= R.plain_thr) {
+            u64 s = lo + R.q_mod_t;
+            hi += (s < lo);
+            lo = s;
+        }
+        out[i] = barrett128(lo, hi, R.limb[j].q, R.ratio0[j], R.ratio1[j]);
+    }
+}
+// w -> (w, floor(w 2^64 / q)); optional second factor: w = a*b mod q first
+__global__ void k_make_shoup(const u64 *a, const u64 *b, W2 *out, unsigned long long total,
+                             unsigned long long b_period, RingDev R)
+{
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t j = (uint32_t)((i >> R.logn) % R.k);
+        const u64 q = R.limb[j].q;
+        u64 w = a[i];
+        if (b) w = mulmod_barrett(w, b[i % b_period], q, R.ratio0[j], R.ratio1[j]);
+        W2 r;
+        r.w = w;
+        r.wp = (u64)((((unsigned __int128)w) << 64) / q);
+        out[i] = r;
+    }
+}
+// poly 0 of every ciphertext +/- scaled plaintext
+template <int SIGN>
+__global__ void k_plain_addsub(u64 *a, const u64 *scaled /*[k][n]*/, unsigned long long n_ct,
+                               uint32_t size, RingDev R)
+{
+    const unsigned long long per = (unsigned long long)R.k * R.n, total = n_ct * per;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long ct = i / per, r = i % per;
+        const u64 q = R.limb[r >> R.logn].q;
+        u64 *p = a + ct * per * size + r;
+        *p = SIGN > 0 ? addmod(*p, scaled[r], q) : submod(*p, scaled[r], q);
+    }
+}
+
+// synthetic inputs: same generator as oracle/fhe_oracle.c orc_fill_uniform
+__global__ void k_fill_uniform(u64 *dst, unsigned long long first_ct, unsigned long long total,
+                               uint32_t size, u64 seed, RingDev R)
+{
+    const unsigned long long per_ct = (unsigned long long)size * R.k * R.n;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const u64 g = first_ct * per_ct + i;  // global element index
+        const u64 q = R.limb[(g >> R.logn) % R.k].q;
+        dst[i] = mulhi_u64(splitmix64(seed + g * 0x9E3779B97F4A7C15ull), q);
+    }
+}
+
+__global__ void k_checksum(const u64 *v, unsigned long long count, unsigned long long *out)
+{
+    u64 acc = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < count;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        acc += splitmix64(v[i] + i * 0x9E3779B97F4A7C15ull);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e__ = (expr);                                                                 \
+        if (e__ != cudaSuccess)                                                                   \
+            return fail(FHE_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+struct fhe_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+    bool own_stream = false;
+    HostRing host;
+    RingDev dev{};
+    W2 *d_tw = nullptr, *d_itw = nullptr;
+    int sm_count = 148;
+    uint64_t launches = 0;
+    uint32_t dct_chunk_blocks = 0;
+    // staging for the host-buffer path
+    static constexpr int kSlots = 3;
+    u64 *stage[kSlots] = {nullptr, nullptr, nullptr};
+    size_t stage_blocks = 0;
+    cudaEvent_t ev_in[kSlots]{}, ev_comp[kSlots]{}, ev_out[kSlots]{};
+    unsigned long long *d_scratch = nullptr;
+    // optional per-kernel timing of the DCT path
+    bool stage_timing = false;
+    std::vector<cudaEvent_t> stage_ev;  // 4 per chunk of the last call
+};
+struct fhe_ptab {
+    fhe_ctx *ctx = nullptr;
+    uint32_t count = 0;
+    W2 *d_ntt = nullptr;     // [count][k][n] Shoup pairs of NTT(lift(plain))
+    u64 *d_scaled = nullptr; // [count][k][n] Delta-scaled coefficients
+    std::vector<uint8_t> is_zero;
+};
+struct fhe_dct_plan {
+    fhe_ctx *ctx = nullptr;
+    W2 *d_c = nullptr;  // [12][k][n]
+    W2 *d_s = nullptr;  // [64][k][n]
+    bool has_quant = false;
+};
+
+static void clear_stage_events(fhe_ctx *c)
+{
+    for (cudaEvent_t e : c->stage_ev) cudaEventDestroy(e);
+    c->stage_ev.clear();
+}
+
+static inline int grid_for(unsigned long long total, int threads, int sm_count)
+{
+    unsigned long long g = (total + threads - 1) / threads;
+    unsigned long long cap = (unsigned long long)sm_count * 16;
+    return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+template <class K>
+static int set_smem(K kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024) CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return FHE_OK;
+}
+
+// dispatch on ring degree: (LOGN, LOGE) pairs with exactly three passes
+#define FHE_DISPATCH_LOGN(logn, CALL)                              \
+    switch (logn) {                                                \
+    case 10: { CALL(10, 4); } break;                               \
+    case 11: { CALL(11, 4); } break;                               \
+    case 12: { CALL(12, 4); } break;                               \
+    case 13: { CALL(13, 5); } break;                               \
+    case 14: { CALL(14, 5); } break;                               \
+    default: return fail(FHE_ERR_UNSUPPORTED, "unsupported ring degree"); \
+    }
+
+template <int LOGN, int LOGE, class RC>
+static int launch_fwd(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, bool full, cudaStream_t st)
+{
+    using S = NttShape<LOGN, LOGE>;
+    const size_t smem = S::SMEM_WORDS * sizeof(u64);
+    if (full) {
+        if (int rc = set_smem(k_ntt_fwd<LOGN, LOGE, RC, true>, smem)) return rc;
+        k_ntt_fwd<LOGN, LOGE, RC, true><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
+    } else {
+        if (int rc = set_smem(k_ntt_fwd<LOGN, LOGE, RC, false>, smem)) return rc;
+        k_ntt_fwd<LOGN, LOGE, RC, false><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
+    }
+    c->launches++;
+    CU_TRY(cudaGetLastError());
+    return FHE_OK;
+}
+template <int LOGN, int LOGE, class RC>
+static int launch_inv(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, cudaStream_t st)
+{
+    using S = NttShape<LOGN, LOGE>;
+    const size_t smem = S::SMEM_WORDS * sizeof(u64);
+    if (int rc = set_smem(k_ntt_inv<LOGN, LOGE, RC>, smem)) return rc;
+    k_ntt_inv<LOGN, LOGE, RC><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
+    c->launches++;
+    CU_TRY(cudaGetLastError());
+    return FHE_OK;
+}
+template <int LOGN, int LOGE, class RC>
+static int launch_mulplain(fhe_ctx *c, const u64 *in, u64 *out, const W2 *tab, uint64_t npoly, cudaStream_t st)
+{
+    using S = NttShape<LOGN, LOGE>;
+    const size_t smem = S::SMEM_WORDS * sizeof(u64);
+    if (int rc = set_smem(k_mulplain<LOGN, LOGE, RC>, smem)) return rc;
+    k_mulplain<LOGN, LOGE, RC><<<(unsigned)npoly, S::T, smem, st>>>(in, out, tab, c->dev);
+    c->launches++;
+    CU_TRY(cudaGetLastError());
+    return FHE_OK;
+}
+
+static int ntt_forward(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, bool full, cudaStream_t st)
+{
+    if (!npoly) return FHE_OK;
+    if (npoly > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many polynomials in one call");
+#define CALL(LN, LE) return launch_fwd<LN, LE, RangeA>(c, in, out, npoly, full, st)
+    FHE_DISPATCH_LOGN(c->host.logn, CALL)
+#undef CALL
+    return FHE_OK;
+}
+static int ntt_inverse(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, cudaStream_t st)
+{
+    if (!npoly) return FHE_OK;
+    if (npoly > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many polynomials in one call");
+#define CALL(LN, LE) return launch_inv<LN, LE, RangeA>(c, in, out, npoly, st)
+    FHE_DISPATCH_LOGN(c->host.logn, CALL)
+#undef CALL
+    return FHE_OK;
+}
+
+static int check_ctx(const fhe_ctx *c)
+{
+    if (!c) return fail(FHE_ERR_INVALID_ARGUMENT, "null context");
+    CU_TRY(cudaSetDevice(c->device));
+    return FHE_OK;
+}
+
+extern "C" {
+
+const char *fhe_last_error(void) { return g_err.c_str(); }
+int fhe_version(void) { return 100; }
+
+int fhe_default_coeff_modulus(uint32_t n, uint64_t *q_out, uint32_t *k_out)
+{
+    // SEAL 2.3.1 coeff_modulus_128 ([SEAL-recall]): the largest primes below 2^55
+    // (2^54 for n = 2048) that are 1 mod 2^18, descending.
+    static const uint64_t P[8] = {0x7fffffff380001ull, 0x7ffffffef00001ull, 0x7ffffffeac0001ull,
+                                  0x7ffffffe700001ull, 0x7ffffffe600001ull, 0x7ffffffe4c0001ull,
+                                  0x7ffffffdec0001ull, 0x7ffffffdd00001ull};
+    if (!q_out || !k_out) return fail(FHE_ERR_INVALID_ARGUMENT, "null output");
+    uint32_t k = 0;
+    switch (n) {
+    case 2048: q_out[0] = 0x3fffffff000001ull; *k_out = 1; return FHE_OK;
+    case 4096: k = 2; break;
+    case 8192: k = 4; break;
+    case 16384: k = 8; break;
+    default: return fail(FHE_ERR_INVALID_ARGUMENT, "coeff_modulus_128 is defined for n in {2048, 4096, 8192, 16384}");
+    }
+    for (uint32_t i = 0; i < k; ++i) q_out[i] = P[i];
+    *k_out = k;
+    return FHE_OK;
+}
+
+int fhe_ctx_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, int device, void *cuda_stream,
+                   fhe_ctx **out)
+{
+    if (!out || !q) return fail(FHE_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    auto c = std::make_unique<fhe_ctx>();
+    std::string err;
+    if (!build_ring(c->host, n, k, q, t, err)) return fail(FHE_ERR_INVALID_ARGUMENT, err);
+    if (c->host.max_qbits > 57)
+        return fail(FHE_ERR_UNSUPPORTED, "coeff_modulus primes above 57 bits are not enabled in this build");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(FHE_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(FHE_ERR_INVALID_ARGUMENT, "device index out of range");
+    c->device = device;
+    CU_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(FHE_ERR_CUDA, "libfhe_b200 is built for sm_100a only");
+    c->sm_count = prop.multiProcessorCount;
+    if (cuda_stream) c->stream = (cudaStream_t)cuda_stream;
+    else {
+        CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    CU_TRY(cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < fhe_ctx::kSlots; ++i) {
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
+    }
+    const size_t tbytes = (size_t)k * n * sizeof(W2);
+    CU_TRY(cudaMalloc(&c->d_tw, tbytes));
+    CU_TRY(cudaMalloc(&c->d_itw, tbytes));
+    CU_TRY(cudaMalloc(&c->d_scratch, 64));
+    std::vector<W2> flat((size_t)k * n);
+    for (uint32_t j = 0; j < k; ++j) std::copy(c->host.limbs[j].tw.begin(), c->host.limbs[j].tw.end(), flat.begin() + (size_t)j * n);
+    CU_TRY(cudaMemcpy(c->d_tw, flat.data(), tbytes, cudaMemcpyHostToDevice));
+    for (uint32_t j = 0; j < k; ++j) std::copy(c->host.limbs[j].itw.begin(), c->host.limbs[j].itw.end(), flat.begin() + (size_t)j * n);
+    CU_TRY(cudaMemcpy(c->d_itw, flat.data(), tbytes, cudaMemcpyHostToDevice));
+    RingDev &D = c->dev;
+    D.n = n; D.logn = c->host.logn; D.k = k; D.t = t; D.plain_thr = c->host.plain_thr; D.q_mod_t = c->host.q_mod_t;
+    for (uint32_t j = 0; j < k; ++j) {
+        D.limb[j] = c->host.limbs[j].dev;
+        D.delta[j] = c->host.limbs[j].delta;
+        D.ratio0[j] = c->host.limbs[j].ratio0;
+        D.ratio1[j] = c->host.limbs[j].ratio1;
+    }
+    D.tw = c->d_tw; D.itw = c->d_itw;
+    *out = c.release();
+    return FHE_OK;
+}
+
+void fhe_ctx_destroy(fhe_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int i = 0; i < fhe_ctx::kSlots; ++i) {
+        if (c->stage[i]) cudaFree(c->stage[i]);
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+        if (c->ev_comp[i]) cudaEventDestroy(c->ev_comp[i]);
+        if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
+    }
+    clear_stage_events(c);
+    cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_scratch);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int fhe_ctx_sync(fhe_ctx *c)
+{
+    if (int rc = check_ctx(c)) return rc;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return FHE_OK;
+}
+
+size_t fhe_ct_bytes(const fhe_ctx *c, uint32_t size) { return c ? (size_t)size * c->host.k * c->host.n * sizeof(u64) : 0; }
+uint64_t fhe_launch_count(const fhe_ctx *c) { return c ? c->launches : 0; }
+int fhe_set_dct_chunk_blocks(fhe_ctx *c, uint32_t blocks)
+{
+    if (!c) return fail(FHE_ERR_INVALID_ARGUMENT, "null context");
+    c->dct_chunk_blocks = blocks;
+    return FHE_OK;
+}
+
+int fhe_set_stage_timing(fhe_ctx *c, int enabled)
+{
+    if (!c) return fail(FHE_ERR_INVALID_ARGUMENT, "null context");
+    c->stage_timing = enabled != 0;
+    if (!enabled) clear_stage_events(c);
+    return FHE_OK;
+}
+int fhe_get_stage_times(fhe_ctx *c, float *ms)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!ms) return fail(FHE_ERR_INVALID_ARGUMENT, "null output");
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    ms[0] = ms[1] = ms[2] = 0.f;
+    for (size_t i = 0; i + 3 < c->stage_ev.size(); i += 4)
+        for (int s = 0; s < 3; ++s) {
+            float t = 0.f;
+            CU_TRY(cudaEventElapsedTime(&t, c->stage_ev[i + s], c->stage_ev[i + s + 1]));
+            ms[s] += t;
+        }
+    return FHE_OK;
+}
+
+int fhe_device_alloc(fhe_ctx *c, size_t bytes, void **dptr)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!dptr) return fail(FHE_ERR_INVALID_ARGUMENT, "null output");
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e != cudaSuccess) return fail(FHE_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return FHE_OK;
+}
+int fhe_device_free(fhe_ctx *c, void *dptr)
+{
+    if (int rc = check_ctx(c)) return rc;
+    CU_TRY(cudaFree(dptr));
+    return FHE_OK;
+}
+int fhe_host_alloc(size_t bytes, void **hptr)
+{
+    if (!hptr) return fail(FHE_ERR_INVALID_ARGUMENT, "null output");
+    cudaError_t e = cudaHostAlloc(hptr, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(FHE_ERR_ALLOC, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return FHE_OK;
+}
+int fhe_host_free(void *hptr)
+{
+    CU_TRY(cudaFreeHost(hptr));
+    return FHE_OK;
+}
+int fhe_upload(fhe_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (int rc = check_ctx(c)) return rc;
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return FHE_OK;
+}
+int fhe_download(fhe_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (int rc = check_ctx(c)) return rc;
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return FHE_OK;
+}
+
+// FractionalEncoder(t, poly_modulus, int_coeffs, frac_coeffs, 2).encode:
+// integer part in binary from x^0 up; i-th fractional binary digit d_i (weight 2^-(i+1)) stored
+// as -d_i at x^(n-1-i) because x^n = -1; negative values negate every digit; all mod t.
+int fhe_frac_encode(uint32_t n, uint64_t t_, double value, uint32_t int_coeffs, uint32_t frac_coeffs,
+                    uint32_t base, uint64_t *plain_out)
+{
+    if (!plain_out) return fail(FHE_ERR_INVALID_ARGUMENT, "null argument");
+    if (base != 2) return fail(FHE_ERR_UNSUPPORTED, "FractionalEncoder base must be 2");
+    if (n < 2 || (n & (n - 1)) || t_ < 2) return fail(FHE_ERR_INVALID_ARGUMENT, "bad ring degree or plain modulus");
+    const u64 t = t_;
+    if ((uint64_t)int_coeffs + frac_coeffs > n) return fail(FHE_ERR_INVALID_ARGUMENT, "integer + fraction coefficient counts exceed n");
+    if (!(value == value) || value > 9.2e18 || value < -9.2e18) return fail(FHE_ERR_INVALID_ARGUMENT, "value out of range");
+    std::memset(plain_out, 0, sizeof(uint64_t) * n);
+    const bool neg = value < 0;
+    const u64 plus = neg ? t - 1 : 1, minus = neg ? 1 : t - 1;
+    double mag = neg ? -value : value;
+    u64 ip = (u64)mag;  // truncation
+    double frac = mag - (double)ip;
+    for (uint32_t i = 0; ip; ++i, ip >>= 1) {
+        if (i >= int_coeffs) return fail(FHE_ERR_INVALID_ARGUMENT, "integer part does not fit int_coeffs");
+        if (ip & 1) plain_out[i] = plus;
+    }
+    for (uint32_t i = 0; i < frac_coeffs && frac != 0; ++i) {
+        frac *= 2.0;
+        if (frac >= 1.0) {
+            frac -= 1.0;
+            plain_out[n - 1 - i] = minus;
+        }
+    }
+    return FHE_OK;
+}
+
+static int elementwise(fhe_ctx *c, int op, u64 *a, const u64 *b, uint64_t n_ct, uint32_t size)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!a || (op != 2 && !b) || size == 0) return fail(FHE_ERR_INVALID_ARGUMENT, "bad argument");
+    const unsigned long long total = (unsigned long long)n_ct * size * c->host.k * c->host.n;
+    if (!total) return FHE_OK;
+    const int g = grid_for(total, 256, c->sm_count);
+    if (op == 0) k_elementwise<0><<<g, 256, 0, c->stream>>>(a, b, total, c->dev);
+    else if (op == 1) k_elementwise<1><<<g, 256, 0, c->stream>>>(a, b, total, c->dev);
+    else k_elementwise<2><<<g, 256, 0, c->stream>>>(a, nullptr, total, c->dev);
+    c->launches++;
+    CU_TRY(cudaGetLastError());
+    return FHE_OK;
+}
+int fhe_add(fhe_ctx *c, uint64_t *a, const uint64_t *b, uint64_t n_ct, uint32_t size) { return elementwise(c, 0, (u64 *)a, (const u64 *)b, n_ct, size); }
+int fhe_sub(fhe_ctx *c, uint64_t *a, const uint64_t *b, uint64_t n_ct, uint32_t size) { return elementwise(c, 1, (u64 *)a, (const u64 *)b, n_ct, size); }
+int fhe_negate(fhe_ctx *c, uint64_t *a, uint64_t n_ct, uint32_t size) { return elementwise(c, 2, (u64 *)a, nullptr, n_ct, size); }
+
+int fhe_ntt_forward(fhe_ctx *c, uint64_t *a, uint64_t npoly)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!a) return fail(FHE_ERR_INVALID_ARGUMENT, "null buffer");
+    return ntt_forward(c, (const u64 *)a, (u64 *)a, npoly, true, c->stream);
+}
+int fhe_ntt_inverse(fhe_ctx *c, uint64_t *a, uint64_t npoly)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!a) return fail(FHE_ERR_INVALID_ARGUMENT, "null buffer");
+    return ntt_inverse(c, (const u64 *)a, (u64 *)a, npoly, c->stream);
+}
+
+// plaintexts (host [count][n]) -> device W2 table [count][k][n] of NTT(lift(plain)) (optionally
+// times a second table, period b_period) and, if d_scaled, the Delta-scaled polys.
+static int build_plain_tables(fhe_ctx *c, const uint64_t *plain, uint32_t count, W2 *d_ntt, u64 *d_scaled,
+                              u64 *d_values_out /* optional [count][k][n] reduced NTT values */)
+{
+    const uint32_t n = c->host.n, k = c->host.k;
+    for (size_t i = 0; i < (size_t)count * n; ++i)
+        if (plain[i] >= c->host.t) return fail(FHE_ERR_INVALID_ARGUMENT, "plaintext coefficient is not below plain_modulus");
+    u64 *d_plain = nullptr, *d_lift = nullptr;
+    const unsigned long long total = (unsigned long long)count * k * n;
+    CU_TRY(cudaMalloc(&d_plain, (size_t)count * n * sizeof(u64)));
+    cudaError_t e = cudaMalloc(&d_lift, total * sizeof(u64));
+    if (e != cudaSuccess) { cudaFree(d_plain); return fail(FHE_ERR_ALLOC, "cudaMalloc failed for plaintext tables"); }
+    int rc = FHE_OK;
+    do {
+        if (cudaMemcpyAsync(d_plain, plain, (size_t)count * n * sizeof(u64), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail(FHE_ERR_CUDA, "plaintext upload failed"); break; }
+        const int g = grid_for(total, 256, c->sm_count);
+        if (d_scaled) { k_plain_scale<<<g, 256, 0, c->stream>>>(d_plain, d_scaled, total, c->dev); c->launches++; }
+        k_plain_lift<<<g, 256, 0, c->stream>>>(d_plain, d_lift, total, c->dev);
+        c->launches++;
+        if ((rc = ntt_forward(c, d_lift, d_lift, (uint64_t)count * k, true, c->stream))) break;
+        if (d_ntt) { k_make_shoup<<<g, 256, 0, c->stream>>>(d_lift, nullptr, d_ntt, total, 1, c->dev); c->launches++; }
+        if (d_values_out && cudaMemcpyAsync(d_values_out, d_lift, total * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { rc = fail(FHE_ERR_CUDA, "table copy failed"); break; }
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = fail(FHE_ERR_CUDA, "plaintext table kernels failed"); break; }
+    } while (0);
+    cudaFree(d_plain);
+    cudaFree(d_lift);
+    return rc;
+}
+
+int fhe_ptab_create(fhe_ctx *c, const uint64_t *plain, uint32_t count, fhe_ptab **out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!plain || !out || !count) return fail(FHE_ERR_INVALID_ARGUMENT, "bad argument");
+    *out = nullptr;
+    auto t = std::make_unique<fhe_ptab>();
+    t->ctx = c;
+    t->count = count;
+    const uint32_t n = c->host.n, k = c->host.k;
+    t->is_zero.assign(count, 1);
+    for (uint32_t p = 0; p < count; ++p)
+        for (uint32_t i = 0; i < n; ++i)
+            if (plain[(size_t)p * n + i]) { t->is_zero[p] = 0; break; }
+    const size_t total = (size_t)count * k * n;
+    CU_TRY(cudaMalloc(&t->d_ntt, total * sizeof(W2)));
+    cudaError_t e = cudaMalloc(&t->d_scaled, total * sizeof(u64));
+    if (e != cudaSuccess) { cudaFree(t->d_ntt); return fail(FHE_ERR_ALLOC, "cudaMalloc failed"); }
+    if (int rc = build_plain_tables(c, plain, count, t->d_ntt, t->d_scaled, nullptr)) {
+        cudaFree(t->d_ntt); cudaFree(t->d_scaled);
+        return rc;
+    }
+    *out = t.release();
+    return FHE_OK;
+}
+void fhe_ptab_destroy(fhe_ptab *t)
+{
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaFree(t->d_ntt);
+    cudaFree(t->d_scaled);
+    delete t;
+}
+
+int fhe_multiply_plain(fhe_ctx *c, uint64_t *a, uint64_t n_ct, uint32_t size, const fhe_ptab *tab, uint32_t index)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!a || !tab || tab->ctx != c || index >= tab->count || !size) return fail(FHE_ERR_INVALID_ARGUMENT, "bad argument");
+    if (tab->is_zero[index]) return fail(FHE_ERR_ZERO_PLAIN, "plain cannot be zero");
+    const uint64_t npoly = n_ct * size * c->host.k;
+    if (!npoly) return FHE_OK;
+    if (npoly > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many polynomials in one call");
+    const W2 *table = tab->d_ntt + (size_t)index * c->host.k * c->host.n;
+#define CALL(LN, LE) return launch_mulplain<LN, LE, RangeA>(c, (const u64 *)a, (u64 *)a, table, npoly, c->stream)
+    FHE_DISPATCH_LOGN(c->host.logn, CALL)
+#undef CALL
+    return FHE_OK;
+}
+
+static int plain_addsub(fhe_ctx *c, int sign, uint64_t *a, uint64_t n_ct, uint32_t size, const fhe_ptab *tab, uint32_t index)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!a || !tab || tab->ctx != c || index >= tab->count || !size) return fail(FHE_ERR_INVALID_ARGUMENT, "bad argument");
+    const unsigned long long total = (unsigned long long)n_ct * c->host.k * c->host.n;
+    if (!total) return FHE_OK;
+    const u64 *scaled = tab->d_scaled + (size_t)index * c->host.k * c->host.n;
+    const int g = grid_for(total, 256, c->sm_count);
+    if (sign > 0) k_plain_addsub<1><<<g, 256, 0, c->stream>>>((u64 *)a, scaled, n_ct, size, c->dev);
+    else k_plain_addsub<-1><<<g, 256, 0, c->stream>>>((u64 *)a, scaled, n_ct, size, c->dev);
+    c->launches++;
+    CU_TRY(cudaGetLastError());
+    return FHE_OK;
+}
+int fhe_add_plain(fhe_ctx *c, uint64_t *a, uint64_t n_ct, uint32_t size, const fhe_ptab *tab, uint32_t index) { return plain_addsub(c, +1, a, n_ct, size, tab, index); }
+int fhe_sub_plain(fhe_ctx *c, uint64_t *a, uint64_t n_ct, uint32_t size, const fhe_ptab *tab, uint32_t index) { return plain_addsub(c, -1, a, n_ct, size, tab, index); }
+
+int fhe_dct_plan_create(fhe_ctx *c, const uint64_t *dct_consts, const uint64_t *eighth, const uint64_t *quant, fhe_dct_plan **out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!dct_consts || !eighth || !out) return fail(FHE_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    const uint32_t n = c->host.n, k = c->host.k;
+    // Evaluator::multiply_plain throws on a zero plaintext: so does plan creation.
+    auto zero = [&](const uint64_t *p) { for (uint32_t i = 0; i < n; ++i) if (p[i]) return false; return true; };
+    for (int i = 0; i < DCT_NCONST; ++i) if (zero(dct_consts + (size_t)i * n)) return fail(FHE_ERR_ZERO_PLAIN, "plain cannot be zero");
+    if (zero(eighth)) return fail(FHE_ERR_ZERO_PLAIN, "plain cannot be zero");
+    if (quant) for (int i = 0; i < 64; ++i) if (zero(quant + (size_t)i * n)) return fail(FHE_ERR_ZERO_PLAIN, "plain cannot be zero");
+    auto p = std::make_unique<fhe_dct_plan>();
+    p->ctx = c;
+    p->has_quant = quant != nullptr;
+    const size_t per = (size_t)k * n;
+    u64 *d_e = nullptr, *d_q = nullptr;
+    CU_TRY(cudaMalloc(&p->d_c, DCT_NCONST * per * sizeof(W2)));
+    CU_TRY(cudaMalloc(&p->d_s, 64 * per * sizeof(W2)));
+    CU_TRY(cudaMalloc(&d_e, per * sizeof(u64)));
+    CU_TRY(cudaMalloc(&d_q, 64 * per * sizeof(u64)));
+    int rc = build_plain_tables(c, dct_consts, DCT_NCONST, p->d_c, nullptr, nullptr);
+    if (!rc) rc = build_plain_tables(c, eighth, 1, nullptr, nullptr, d_e);
+    if (!rc && quant) rc = build_plain_tables(c, quant, 64, nullptr, nullptr, d_q);
+    if (!rc) {
+        // merged scale constants: s[i] = NTT(0.125) * NTT(1/quant[i]) (ring multiplication is
+        // associative, so (x * 0.125) * (1/quant) == x * (0.125 * 1/quant) exactly), or NTT(0.125).
+        const unsigned long long total = 64ull * per;
+        const int g = grid_for(total, 256, c->sm_count);
+        if (quant) k_make_shoup<<<g, 256, 0, c->stream>>>(d_q, d_e, p->d_s, total, per, c->dev);
+        else {
+            // replicate the eighth table 64 times
+            for (int i = 0; i < 64; ++i) cudaMemcpyAsync(d_q + (size_t)i * per, d_e, per * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream);
+            k_make_shoup<<<g, 256, 0, c->stream>>>(d_q, nullptr, p->d_s, total, 1, c->dev);
+        }
+        c->launches++;
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = fail(FHE_ERR_CUDA, "scale table kernel failed");
+    }
+    cudaFree(d_e);
+    cudaFree(d_q);
+    if (rc) { cudaFree(p->d_c); cudaFree(p->d_s); return rc; }
+    *out = p.release();
+    return FHE_OK;
+}
+void fhe_dct_plan_destroy(fhe_dct_plan *p)
+{
+    if (!p) return;
+    cudaSetDevice(p->ctx->device);
+    cudaFree(p->d_c);
+    cudaFree(p->d_s);
+    delete p;
+}
+
+// three kernels per chunk: forward NTT (in -> out), pointwise DCT in place, inverse NTT in place
+static int dct_chunk(fhe_ctx *c, const fhe_dct_plan *plan, const u64 *in, u64 *out, uint64_t nblocks, cudaStream_t st)
+{
+    const uint32_t n = c->host.n, k = c->host.k;
+    const uint64_t npoly = nblocks * 64 * 2 * k;
+    auto mark = [&]() -> int {
+        if (!c->stage_timing) return FHE_OK;
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreate(&e));
+        c->stage_ev.push_back(e);
+        CU_TRY(cudaEventRecord(e, st));
+        return FHE_OK;
+    };
+    if (int rc = mark()) return rc;
+    if (int rc = ntt_forward(c, in, out, npoly, true, st)) return rc;
+    if (int rc = mark()) return rc;
+    const unsigned long long nunits = nblocks * 2;
+    const int upc = 16;
+    const unsigned long long ugs = (nunits + upc - 1) / upc;
+    const unsigned long long grid = ugs * k * (n / DCT_TILE);
+    if (grid > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many blocks in one chunk");
+    k_dct_pointwise<<<(unsigned)grid, 256, 0, st>>>(out, plan->d_c, plan->d_s, c->dev, nunits, upc);
+    c->launches++;
+    CU_TRY(cudaGetLastError());
+    if (int rc = mark()) return rc;
+    if (int rc = ntt_inverse(c, out, out, npoly, st)) return rc;
+    return mark();
+}
+
+static const uint64_t kMaxChunkBlocks = 1ull << 20;
+
+int fhe_dct8x8_quantize(fhe_ctx *c, const fhe_dct_plan *plan, const uint64_t *d_in, uint64_t *d_out, uint64_t nblocks)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!plan || plan->ctx != c || !d_in || !d_out) return fail(FHE_ERR_INVALID_ARGUMENT, "bad argument");
+    const size_t blk_words = (size_t)64 * 2 * c->host.k * c->host.n;
+    clear_stage_events(c);
+    uint64_t chunk = c->dct_chunk_blocks ? c->dct_chunk_blocks : nblocks;
+    if (chunk > kMaxChunkBlocks / c->host.k) chunk = kMaxChunkBlocks / c->host.k;
+    for (uint64_t b = 0; b < nblocks; b += chunk) {
+        const uint64_t nb = nblocks - b < chunk ? nblocks - b : chunk;
+        if (int rc = dct_chunk(c, plan, (const u64 *)d_in + b * blk_words, (u64 *)d_out + b * blk_words, nb, c->stream)) return rc;
+    }
+    return FHE_OK;
+}
+
+int fhe_dct8x8_quantize_host(fhe_ctx *c, const fhe_dct_plan *plan, const uint64_t *h_in, uint64_t *h_out, uint64_t nblocks)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!plan || plan->ctx != c || !h_in || !h_out) return fail(FHE_ERR_INVALID_ARGUMENT, "bad argument");
+    if (!nblocks) return FHE_OK;
+    clear_stage_events(c);
+    const size_t blk_bytes = (size_t)64 * 2 * c->host.k * c->host.n * sizeof(u64);
+    // staging slots of up to 256 MiB
+    uint64_t sb = (256ull << 20) / blk_bytes;
+    if (sb < 1) sb = 1;
+    if (sb > nblocks) sb = nblocks;
+    if (c->stage_blocks < sb) {
+        for (int i = 0; i < fhe_ctx::kSlots; ++i) {
+            if (c->stage[i]) cudaFree(c->stage[i]);
+            c->stage[i] = nullptr;
+            cudaError_t e = cudaMalloc(&c->stage[i], sb * blk_bytes);
+            if (e != cudaSuccess) { c->stage_blocks = 0; return fail(FHE_ERR_ALLOC, "cudaMalloc failed for staging"); }
+        }
+        c->stage_blocks = sb;
+    }
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    uint64_t idx = 0;
+    for (uint64_t b = 0; b < nblocks; b += sb, ++idx) {
+        const int s = (int)(idx % fhe_ctx::kSlots);
+        const uint64_t nb = nblocks - b < sb ? nblocks - b : sb;
+        const char *src = (const char *)h_in + b * blk_bytes;
+        char *dst = (char *)h_out + b * blk_bytes;
+        if (idx >= (uint64_t)fhe_ctx::kSlots) CU_TRY(cudaStreamWaitEvent(c->s_in, c->ev_out[s], 0));  // slot drained
+        CU_TRY(cudaMemcpyAsync(c->stage[s], src, nb * blk_bytes, cudaMemcpyHostToDevice, c->s_in));
+        CU_TRY(cudaEventRecord(c->ev_in[s], c->s_in));
+        CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_in[s], 0));
+        if (int rc = dct_chunk(c, plan, c->stage[s], c->stage[s], nb, c->stream)) return rc;
+        CU_TRY(cudaEventRecord(c->ev_comp[s], c->stream));
+        CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_comp[s], 0));
+        CU_TRY(cudaMemcpyAsync(dst, c->stage[s], nb * blk_bytes, cudaMemcpyDeviceToHost, c->s_out));
+        CU_TRY(cudaEventRecord(c->ev_out[s], c->s_out));
+    }
+    CU_TRY(cudaStreamSynchronize(c->s_out));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return FHE_OK;
+}
+
+int fhe_fill_uniform(fhe_ctx *c, uint64_t *d_dst, uint64_t first_ct, uint64_t n_ct, uint32_t size, uint64_t seed)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!d_dst || !size) return fail(FHE_ERR_INVALID_ARGUMENT, "bad argument");
+    const unsigned long long total = (unsigned long long)n_ct * size * c->host.k * c->host.n;
+    if (!total) return FHE_OK;
+    k_fill_uniform<<<grid_for(total, 256, c->sm_count), 256, 0, c->stream>>>((u64 *)d_dst, first_ct, total, size, seed, c->dev);
+    c->launches++;
+    CU_TRY(cudaGetLastError());
+    return FHE_OK;
+}
+
+int fhe_checksum(fhe_ctx *c, const uint64_t *d, uint64_t count, uint64_t *out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!d || !out) return fail(FHE_ERR_INVALID_ARGUMENT, "null argument");
+    CU_TRY(cudaMemsetAsync(c->d_scratch, 0, 8, c->stream));
+    if (count) {
+        k_checksum<<<grid_for(count, 256, c->sm_count), 256, 0, c->stream>>>((const u64 *)d, count, c->d_scratch);
+        c->launches++;
+    }
+    unsigned long long h = 0;
+    CU_TRY(cudaMemcpyAsync(&h, c->d_scratch, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *out = h;
+    return FHE_OK;
+}
+
+}  // extern "C"

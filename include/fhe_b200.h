@@ -1,0 +1,152 @@
+/*
+ * fhe_b200.h -- C-ABI of libfhe_b200.so: the B200-native BFV ciphertext-arithmetic hot path
+ * that homo/server_jpeg.cpp (and, next, server_resize.cpp / server_decode.cpp) of
+ * wfus/Fully-Homomorphic-Image-Processing drive through seal::Evaluator.
+ *
+ * The reference has no FFI layer: its boundary is the C++ calling convention between the
+ * image-op headers (homo/fhe_image.h, fhe_resize.h, fhe_decode.h) and seal::Evaluator /
+ * seal::FractionalEncoder.  Each entry point below names the reference
+ * interface it replaces (file:line under /root/reference).  INTEGRATION.md shows the binding a
+ * maintainer adds on the reference side (host/seal_shim.hpp gives seal-shaped C++ classes over
+ * this ABI so fhe_image.h-style graphs compile unchanged in spirit).
+ *
+ * Conventions: extern "C", opaque handles, plain pointers and sizes; int status return
+ * (0 = FHE_OK, negative = error, text via fhe_last_error(), thread-local); no exceptions cross
+ * the ABI; the caller owns every buffer it passes; one CUDA stream per context, calls are
+ * asynchronous with respect to the host unless stated (fhe_ctx_sync waits); a context is
+ * thread-compatible (one thread at a time), there is no global mutable state.
+ *
+ * Ciphertext layout (host and device): [ciphertext][poly][limb][n] uint64, residues in
+ * [0, q_limb).  A size-2 ciphertext at n=4096, k=2 is 131072 bytes.  (SEAL 2.3 stores n+1
+ * coefficients per limb with a zero top coefficient; drop it when importing, Appendix A.1.)
+ * Plaintext layout: n uint64 coefficients in [0, t).
+ *
+ * There is NO CPU fallback: every compute entry point fails with FHE_ERR_CUDA when no CUDA
+ * device is usable.
+ */
+#ifndef FHE_B200_H
+#define FHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FHE_OK 0
+#define FHE_ERR_INVALID_ARGUMENT (-1) /* seal: std::invalid_argument */
+#define FHE_ERR_CUDA (-2)
+#define FHE_ERR_UNSUPPORTED (-3)
+#define FHE_ERR_ZERO_PLAIN (-4) /* seal: multiply_plain throws on an all-zero plaintext */
+#define FHE_ERR_ALLOC (-5)
+
+typedef struct fhe_ctx fhe_ctx;           /* seal::SEALContext + seal::Evaluator */
+typedef struct fhe_ptab fhe_ptab;         /* a set of pre-transformed seal::Plaintext */
+typedef struct fhe_dct_plan fhe_dct_plan; /* tables of encrypted_dct + quantize_fhe */
+
+const char *fhe_last_error(void);
+int fhe_version(void);
+
+/* ---- context -------------------------------------------------------------------------------
+ * Replaces EncryptionParameters / SEALContext / Evaluator construction,
+ * homo/server_jpeg.cpp:74-80,93 (set_poly_modulus "1x^n + 1", set_coeff_modulus, set_plain_modulus).
+ * q: k distinct primes < 2^61, each 1 mod 2n.  cuda_stream: a cudaStream_t to enqueue on, or
+ * NULL to let the context create its own. */
+int fhe_ctx_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, int device,
+                   void *cuda_stream, fhe_ctx **out);
+void fhe_ctx_destroy(fhe_ctx *ctx);
+int fhe_ctx_sync(fhe_ctx *ctx);
+/* seal::coeff_modulus_128(n), server_jpeg.cpp:78 ([SEAL-recall] chain). */
+int fhe_default_coeff_modulus(uint32_t n, uint64_t *q_out, uint32_t *k_out);
+/* bytes of one ciphertext of `size` polys */
+size_t fhe_ct_bytes(const fhe_ctx *ctx, uint32_t size);
+
+/* ---- buffers ------------------------------------------------------------------------------ */
+int fhe_device_alloc(fhe_ctx *ctx, size_t bytes, void **dptr);
+int fhe_device_free(fhe_ctx *ctx, void *dptr);
+int fhe_host_alloc(size_t bytes, void **hptr); /* pinned */
+int fhe_host_free(void *hptr);
+int fhe_upload(fhe_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);   /* synchronous */
+int fhe_download(fhe_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* synchronous */
+
+/* ---- encoder (host logic) -----------------------------------------------------------------
+ * seal::FractionalEncoder(plain_modulus, poly_modulus, int_coeffs, frac_coeffs, base).encode,
+ * constructed at server_jpeg.cpp:100 and called at 43 sites of fhe_image.h (e.g. :221).
+ * base must be 2 (the reference's --base override is dead code, server_jpeg.cpp:66).
+ * Pure host logic (n = ring degree, t = plain modulus): needs no device. */
+int fhe_frac_encode(uint32_t n, uint64_t t, double value, uint32_t int_coeffs, uint32_t frac_coeffs,
+                    uint32_t base, uint64_t *plain_out /* n */);
+
+/* ---- Evaluator: exact ring ops on device arrays of n_ct ciphertexts -----------------------
+ * Evaluator::add / sub / negate, e.g. fhe_image.h:207-208, fhe_resize.h:196.  In place on a. */
+int fhe_add(fhe_ctx *ctx, uint64_t *a, const uint64_t *b, uint64_t n_ct, uint32_t size);
+int fhe_sub(fhe_ctx *ctx, uint64_t *a, const uint64_t *b, uint64_t n_ct, uint32_t size);
+int fhe_negate(fhe_ctx *ctx, uint64_t *a, uint64_t n_ct, uint32_t size);
+
+/* Plaintext tables: for each of `count` plaintexts (host, [count][n], coefficients < t) the
+ * centred lift is transformed once and kept in Shoup form, with its Delta-scaled polynomial
+ * (Encryptor::preencrypt) beside it.  Replaces the per-call work inside
+ * Evaluator::multiply_plain / add_plain / sub_plain. */
+int fhe_ptab_create(fhe_ctx *ctx, const uint64_t *plain_coeffs, uint32_t count, fhe_ptab **out);
+void fhe_ptab_destroy(fhe_ptab *tab);
+/* Evaluator::multiply_plain(ct, plain), fhe_image.h:221 and 41 more: every ciphertext of the
+ * array times plaintext `index` (one fused NTT -> dyadic -> inverse-NTT kernel per limb-poly).
+ * FHE_ERR_ZERO_PLAIN if that plaintext is zero. */
+int fhe_multiply_plain(fhe_ctx *ctx, uint64_t *a, uint64_t n_ct, uint32_t size, const fhe_ptab *tab,
+                       uint32_t index);
+/* Evaluator::add_plain / sub_plain (fhe_resize.h:196 / fhe_image.h:317): poly 0 +/- Delta*m. */
+int fhe_add_plain(fhe_ctx *ctx, uint64_t *a, uint64_t n_ct, uint32_t size, const fhe_ptab *tab,
+                  uint32_t index);
+int fhe_sub_plain(fhe_ctx *ctx, uint64_t *a, uint64_t n_ct, uint32_t size, const fhe_ptab *tab,
+                  uint32_t index);
+
+/* util/smallntt ntt_negacyclic_harvey / inverse ([SEAL-recall]) over n_limbpolys consecutive
+ * [limb-cycled] polynomials, in place.  The NTT-domain coefficient order is internal to this
+ * library (a fixed permutation of SEAL's bit-reversed order, see csrc/ntt.cuh). */
+int fhe_ntt_forward(fhe_ctx *ctx, uint64_t *a, uint64_t n_limbpolys);
+int fhe_ntt_inverse(fhe_ctx *ctx, uint64_t *a, uint64_t n_limbpolys);
+
+/* ---- the north-star path: encrypted 8x8 DCT + quantize ------------------------------------
+ * Plan = the 12 distinct constants of encrypted_dct in the order of fhe_image.h:221-236
+ * (0.541196100, 0.765366865, -1.847759065, 1.175875602, 0.298631336, 2.053119869, 3.072711026,
+ * 1.501321110, -0.899976223, -2.562915447, -1.961570560, -0.390180644) as plaintexts
+ * [12][n], encode(0.125) (:259) [n], and optionally the 64 plaintexts encode(1/quant[i])
+ * of quantize_fhe (:301) [64][n]; quant == NULL gives encrypted_dct alone. */
+int fhe_dct_plan_create(fhe_ctx *ctx, const uint64_t *dct_consts, const uint64_t *eighth,
+                        const uint64_t *quant, fhe_dct_plan **out);
+void fhe_dct_plan_destroy(fhe_dct_plan *plan);
+/* encrypted_dct(data, ...) [+ quantize_fhe(data, quant, ...)] on nblocks blocks, each 64
+ * size-2 ciphertexts row-major (fhe_image.h:192-199, 294-298; block loop server_jpeg.cpp:113-138).
+ * d_in, d_out: device, [block][64][2][k][n]; may alias (in place, as in the reference). */
+int fhe_dct8x8_quantize(fhe_ctx *ctx, const fhe_dct_plan *plan, const uint64_t *d_in,
+                        uint64_t *d_out, uint64_t nblocks);
+/* Same with HOST buffers (what server_jpeg.cpp holds after Ciphertext::load, :115-124):
+ * chunks are copied in, transformed and copied back on three overlapped streams.
+ * Synchronous: returns when h_out is complete.  Pinned buffers (fhe_host_alloc) run faster. */
+int fhe_dct8x8_quantize_host(fhe_ctx *ctx, const fhe_dct_plan *plan, const uint64_t *h_in,
+                             uint64_t *h_out, uint64_t nblocks);
+
+/* ---- synthetic inputs / checks ---------------------------------------------
+ * Counter-based SplitMix64 -> uniform residues, same generator as oracle/fhe_oracle.c. */
+int fhe_fill_uniform(fhe_ctx *ctx, uint64_t *d_dst, uint64_t first_ct, uint64_t n_ct, uint32_t size,
+                     uint64_t seed);
+/* order-sensitive 64-bit checksum of a device u64 array; synchronous. */
+int fhe_checksum(fhe_ctx *ctx, const uint64_t *d, uint64_t count, uint64_t *out);
+
+/* ---- tuning / introspection ---------------------------------------------------------------
+ * Kernels this library launched on this context since creation (all streams). */
+uint64_t fhe_launch_count(const fhe_ctx *ctx);
+/* blocks per internal chunk of fhe_dct8x8_quantize (0 = whole call in one chunk). */
+int fhe_set_dct_chunk_blocks(fhe_ctx *ctx, uint32_t blocks);
+/* Per-kernel device timing of fhe_dct8x8_quantize (CUDA events recorded on the context's stream
+ * between its kernels; the reference times the same region with steady_clock, fhe_image.h:200,285).
+ * fhe_get_stage_times waits for the stream and returns the milliseconds of the LAST call:
+ * ms[0] forward NTT, ms[1] pointwise DCT(+quantize), ms[2] inverse NTT (summed over chunks). */
+int fhe_set_stage_timing(fhe_ctx *ctx, int enabled);
+int fhe_get_stage_times(fhe_ctx *ctx, float *ms /* 3 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,175 @@
+// emu.cpp -- CPU emulation of the CUDA thread bodies (tests only).
+//
+// There is no GPU in the development container, so the __host__ __device__ kernel bodies in
+// csrc/ntt.cuh and csrc/dct.cuh are executed here thread by thread (all tau of a pass, then
+// the next pass = what __syncthreads() orders on the device).  This checks the index math,
+// twiddle indexing, lazy-range bookkeeping and table conventions against the oracle before any
+// GPU time is spent.  It is NOT a product code path: nothing in the package loads this library.
+#include <cstring>
+#include <memory>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../fully-homomorphic-image-processing_b200/csrc/dct.cuh"
+#include "../../fully-homomorphic-image-processing_b200/csrc/ntt.cuh"
+#include "../../fully-homomorphic-image-processing_b200/csrc/ring_host.hpp"
+
+using namespace fhe;
+
+template <int V> using ic = std::integral_constant<int, V>;
+
+template <int LOGN, int LOGE, class RC>
+static void emu_fwd(const HostLimb &L, const u64 *in, u64 *out, bool full)
+{
+    using S = NttShape<LOGN, LOGE>;
+    std::vector<u64> smem(S::SMEM_WORDS), tmp(in, in + S::N);
+    auto pass = [&](auto tag) {
+        constexpr int P = decltype(tag)::value;
+        for (int tau = 0; tau < S::T; ++tau) {
+            if (full) ntt_fwd_pass<LOGN, LOGE, P, RC, true>(tau, tmp.data(), out, smem.data(), L.tw.data(), L.dev);
+            else ntt_fwd_pass<LOGN, LOGE, P, RC, false>(tau, tmp.data(), out, smem.data(), L.tw.data(), L.dev);
+        }
+    };
+    pass(ic<0>{});
+    if constexpr (S::NPASS > 1) pass(ic<1>{});
+    if constexpr (S::NPASS > 2) pass(ic<2>{});
+    if constexpr (S::NPASS > 3) pass(ic<3>{});
+}
+template <int LOGN, int LOGE, class RC>
+static void emu_inv(const HostLimb &L, const u64 *in, u64 *out)
+{
+    using S = NttShape<LOGN, LOGE>;
+    std::vector<u64> smem(S::SMEM_WORDS), tmp(in, in + S::N);
+    auto pass = [&](auto tag) {
+        constexpr int P = decltype(tag)::value;
+        for (int tau = 0; tau < S::T; ++tau)
+            ntt_inv_pass<LOGN, LOGE, P, RC>(tau, tmp.data(), out, smem.data(), L.itw.data(), L.dev);
+    };
+    if constexpr (S::NPASS > 3) pass(ic<3>{});
+    if constexpr (S::NPASS > 2) pass(ic<2>{});
+    if constexpr (S::NPASS > 1) pass(ic<1>{});
+    pass(ic<0>{});
+}
+
+template <class RC>
+static int fwd_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, bool full)
+{
+    const HostLimb &L = R.limbs[j];
+    switch (R.logn) {
+    case 10: emu_fwd<10, 4, RC>(L, in, out, full); return 0;
+    case 11: emu_fwd<11, 4, RC>(L, in, out, full); return 0;
+    case 12: emu_fwd<12, 4, RC>(L, in, out, full); return 0;
+    case 13: emu_fwd<13, 5, RC>(L, in, out, full); return 0;
+    case 14: emu_fwd<14, 5, RC>(L, in, out, full); return 0;
+    default: return -1;
+    }
+}
+template <class RC>
+static int inv_dispatch(const HostRing &R, int j, const u64 *in, u64 *out)
+{
+    const HostLimb &L = R.limbs[j];
+    switch (R.logn) {
+    case 10: emu_inv<10, 4, RC>(L, in, out); return 0;
+    case 11: emu_inv<11, 4, RC>(L, in, out); return 0;
+    case 12: emu_inv<12, 4, RC>(L, in, out); return 0;
+    case 13: emu_inv<13, 5, RC>(L, in, out); return 0;
+    case 14: emu_inv<14, 5, RC>(L, in, out); return 0;
+    default: return -1;
+    }
+}
+
+extern "C" {
+
+void *emu_ring_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, char *err, int errlen)
+{
+    auto R = std::make_unique<HostRing>();
+    std::string e;
+    if (!build_ring(*R, n, k, q, t, e)) {
+        if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
+        return nullptr;
+    }
+    return R.release();
+}
+void emu_ring_destroy(void *r) { delete (HostRing *)r; }
+uint64_t emu_psi(void *r, int j) { return ((HostRing *)r)->limbs[j].psi; }
+uint64_t emu_delta(void *r, int j) { return ((HostRing *)r)->limbs[j].delta; }
+uint64_t emu_q_mod_t(void *r) { return ((HostRing *)r)->q_mod_t; }
+
+// range_class: 0 = RangeA (q < 2^57), 1 = RangeB (q < 2^61)
+int emu_ntt_forward(void *r, int j, const uint64_t *in, uint64_t *out, int full, int range_class)
+{
+    const HostRing &R = *(HostRing *)r;
+    return range_class ? fwd_dispatch<RangeB>(R, j, (const u64 *)in, (u64 *)out, full)
+                       : fwd_dispatch<RangeA>(R, j, (const u64 *)in, (u64 *)out, full);
+}
+int emu_ntt_inverse(void *r, int j, const uint64_t *in, uint64_t *out, int range_class)
+{
+    const HostRing &R = *(HostRing *)r;
+    return range_class ? inv_dispatch<RangeB>(R, j, (const u64 *)in, (u64 *)out)
+                       : inv_dispatch<RangeA>(R, j, (const u64 *)in, (u64 *)out);
+}
+
+// Emulated fused DCT(+quantize) on `nblocks` blocks: forward NTT of every limb-poly, pointwise
+// row/column phases per (unit, limb, tile), inverse NTT.  plains: [12][n] DCT constants,
+// eighth: [n], quant: [64][n] or NULL.  data: [block][64][2][k][n], in place.
+int emu_dct_quant(void *r, uint64_t *data_, uint64_t nblocks, const uint64_t *plains,
+                  const uint64_t *eighth, const uint64_t *quant)
+{
+    const HostRing &R = *(HostRing *)r;
+    u64 *data = (u64 *)data_;
+    const uint32_t n = R.n, k = R.k;
+    // plan tables in the permuted NTT domain
+    auto lift_ntt = [&](const uint64_t *plain, uint32_t j, std::vector<u64> &out) {
+        out.assign(n, 0);
+        for (uint32_t i = 0; i < n; ++i) out[i] = plain[i] >= R.plain_thr ? plain[i] + (R.limbs[j].q - R.t) : plain[i];
+        fwd_dispatch<RangeA>(R, j, out.data(), out.data(), true);
+    };
+    std::vector<std::vector<W2>> ctab(k), stab(k);
+    std::vector<u64> a, b;
+    for (uint32_t j = 0; j < k; ++j) {
+        u64 q = R.limbs[j].q;
+        ctab[j].resize((size_t)DCT_NCONST * n);
+        stab[j].resize((size_t)64 * n);
+        for (int c = 0; c < DCT_NCONST; ++c) {
+            lift_ntt(plains + (size_t)c * n, j, a);
+            for (uint32_t i = 0; i < n; ++i) ctab[j][(size_t)c * n + i] = h_shoup(a[i], q);
+        }
+        lift_ntt(eighth, j, a);
+        for (int s = 0; s < 64; ++s) {
+            if (quant) lift_ntt(quant + (size_t)s * n, j, b);
+            for (uint32_t i = 0; i < n; ++i)
+                stab[j][(size_t)s * n + i] = h_shoup(quant ? h_mulmod(a[i], b[i], q) : a[i], q);
+        }
+    }
+    const size_t ct_stride = (size_t)2 * k * n;
+    for (uint64_t blk = 0; blk < nblocks; ++blk) {
+        u64 *B = data + blk * 64 * ct_stride;
+        for (size_t lp = 0; lp < (size_t)64 * 2 * k; ++lp)
+            fwd_dispatch<RangeA>(R, lp % k, B + lp * n, B + lp * n, true);
+        std::vector<u64> sbuf(64 * DCT_TILE);
+        for (uint32_t p = 0; p < 2; ++p)
+            for (uint32_t j = 0; j < k; ++j)
+                for (uint32_t tile = 0; tile < n / DCT_TILE; ++tile) {
+                    u64 *base = B + ((size_t)p * k + j) * n + (size_t)tile * DCT_TILE;
+                    u64 q = R.limbs[j].q;
+                    for (int w = 0; w < 8; ++w)
+                        for (int lane = 0; lane < DCT_TILE; ++lane) {
+                            W2 c[DCT_NCONST];
+                            for (int ci = 0; ci < DCT_NCONST; ++ci) c[ci] = ctab[j][(size_t)ci * n + tile * DCT_TILE + lane];
+                            dct_row_phase(w, lane, base, ct_stride, sbuf.data(), c, q);
+                        }
+                    for (int w = 0; w < 8; ++w)
+                        for (int lane = 0; lane < DCT_TILE; ++lane) {
+                            W2 c[DCT_NCONST], s[8];
+                            for (int ci = 0; ci < DCT_NCONST; ++ci) c[ci] = ctab[j][(size_t)ci * n + tile * DCT_TILE + lane];
+                            for (int i = 0; i < 8; ++i) s[i] = stab[j][(size_t)(8 * i + w) * n + tile * DCT_TILE + lane];
+                            dct_col_phase(w, lane, base, ct_stride, sbuf.data(), c, s, q);
+                        }
+                }
+        for (size_t lp = 0; lp < (size_t)64 * 2 * k; ++lp)
+            inv_dispatch<RangeA>(R, lp % k, B + lp * n, B + lp * n);
+    }
+    return 0;
+}
+}
