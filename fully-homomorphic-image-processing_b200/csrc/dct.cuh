@@ -8,8 +8,9 @@
 // (SURVEY.md 0.6, 7.3).  Canonical residues are unique, hence the result is bit-identical to
 // SEAL's op-by-op evaluation.  The butterfly network below is the reference's own (the LLM
 // "islow" network, mirror of dct() at fhe_image.h:400-484); only the arithmetic is lazy:
-// additions never reduce, subtractions add a compile-time multiple of q, and the Shoup
-// multiplications by the 12 constants / 64 merged scale factors bring values back under 2q.
+// additions never reduce, subtractions add a compile-time multiple of q, and the multiplications
+// (modarith.cuh mulc) by the 12 constants / 64 merged scale factors bring values back under 5q.
+// With q < 2^55 (256 q <= 2^63) the whole 2-D network needs no reduction step at all.
 #pragma once
 #include "modarith.cuh"
 
@@ -22,11 +23,12 @@ enum DctConst {
     DCT_NCONST
 };
 
-// One 1-D pass on d[0..7].  Inputs < INB*q.  Outputs: d0,d4 < 8*INB*q; d2,d6 < 4q; odd < 8q.
-// Needs 8*INB*q < 2^64.
+// One 1-D pass on d[0..7].  Inputs < INB*q.  Outputs: d0,d4 < 8*INB*q; d2,d6 < 10q; odd < 20q.
+// Needs 8*INB <= FHE_BMAX (every mulc argument stays below 2^63).
 template <int INB>
-FHE_HD void dct8_pass(u64 *d, const W2 *c, u64 q)
+FHE_HD void dct8_pass(u64 *d, const W2 *c, u64 q, u64 n2q)
 {
+    static_assert(8 * INB <= 256, "dct8_pass: lazy bound exceeds 2^63");
     const u64 o1 = (u64)INB * q, o2 = 2 * o1, o4 = 4 * o1;
     u64 tmp0 = d[0] + d[7], tmp7 = d[0] - d[7] + o1;
     u64 tmp1 = d[1] + d[6], tmp6 = d[1] - d[6] + o1;
@@ -36,20 +38,20 @@ FHE_HD void dct8_pass(u64 *d, const W2 *c, u64 q)
     u64 tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2 + o2;
     d[0] = tmp10 + tmp11;
     d[4] = tmp10 - tmp11 + o4;
-    u64 z1 = shoup_lazy(tmp12 + tmp13, c[C_0541196100], q);
-    d[2] = z1 + shoup_lazy(tmp13, c[C_0765366865], q);
-    d[6] = z1 + shoup_lazy(tmp12, c[C_M1847759065], q);
+    u64 z1 = mulc(tmp12 + tmp13, c[C_0541196100], n2q);
+    d[2] = z1 + mulc(tmp13, c[C_0765366865], n2q);
+    d[6] = z1 + mulc(tmp12, c[C_M1847759065], n2q);
     z1 = tmp4 + tmp7;
     u64 z2 = tmp5 + tmp6, z3 = tmp4 + tmp6, z4 = tmp5 + tmp7;
-    u64 z5 = shoup_lazy(z3 + z4, c[C_1175875602], q);
-    tmp4 = shoup_lazy(tmp4, c[C_0298631336], q);
-    tmp5 = shoup_lazy(tmp5, c[C_2053119869], q);
-    tmp6 = shoup_lazy(tmp6, c[C_3072711026], q);
-    tmp7 = shoup_lazy(tmp7, c[C_1501321110], q);
-    z1 = shoup_lazy(z1, c[C_M0899976223], q);
-    z2 = shoup_lazy(z2, c[C_M2562915447], q);
-    z3 = shoup_lazy(z3, c[C_M1961570560], q) + z5;
-    z4 = shoup_lazy(z4, c[C_M0390180644], q) + z5;
+    u64 z5 = mulc(z3 + z4, c[C_1175875602], n2q);
+    tmp4 = mulc(tmp4, c[C_0298631336], n2q);
+    tmp5 = mulc(tmp5, c[C_2053119869], n2q);
+    tmp6 = mulc(tmp6, c[C_3072711026], n2q);
+    tmp7 = mulc(tmp7, c[C_1501321110], n2q);
+    z1 = mulc(z1, c[C_M0899976223], n2q);
+    z2 = mulc(z2, c[C_M2562915447], n2q);
+    z3 = mulc(z3, c[C_M1961570560], n2q) + z5;
+    z4 = mulc(z4, c[C_M0390180644], n2q) + z5;
     d[7] = tmp4 + z1 + z3;
     d[5] = tmp5 + z2 + z4;
     d[3] = tmp6 + z2 + z3;
@@ -61,32 +63,35 @@ FHE_HD void dct8_pass(u64 *d, const W2 *c, u64 q)
 // lane = NTT position.  The 8x8 transposition between the phases goes through shared memory
 // (64 x 32 u64 = 16 KiB per buffer, conflict-free: a warp always touches 32 consecutive words).
 constexpr int DCT_TILE = 32;
+// bound (units of q) of the forward-NTT output the row phase reads (NTT_OUT_REDUCED: [0, 4q))
+constexpr int DCT_ROW_INB = 4;
 
 // Row phase for (row r, lane): block rows are ciphertexts 8r..8r+7 (fhe_image.h:192-195).
 // in: pointer to (ct 0, this poly, this limb, first position of the tile); ct_stride in u64.
 FHE_HD void dct_row_phase(int r, int lane, const u64 *__restrict__ in, size_t ct_stride, u64 *sbuf,
-                          const W2 *c, u64 q)
+                          const W2 *c, u64 q, u64 n2q)
 {
     u64 d[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = in[(size_t)(8 * r + i) * ct_stride + lane];
-    dct8_pass<1>(d, c, q);
+    dct8_pass<DCT_ROW_INB>(d, c, q, n2q);
 #pragma unroll
     for (int i = 0; i < 8; ++i) sbuf[(8 * r + i) * DCT_TILE + lane] = d[i];
 }
 
 // Column phase for (column col, lane): 1-D pass down the column, then one multiplication per
 // output by the merged scale constant  s[i] = NTT(0.125) * NTT(1/quant[8i+col])  (or NTT(0.125)
-// alone when no quantisation table is attached).  Output < 2q (inverse-NTT input range).
+// alone when no quantisation table is attached), times n^-1 so the inverse NTT that follows skips
+// its own scaling.  Output < 5q (inverse-NTT input range).
 FHE_HD void dct_col_phase(int col, int lane, u64 *__restrict__ out, size_t ct_stride, const u64 *sbuf,
-                          const W2 *c, const W2 *s, u64 q)
+                          const W2 *c, const W2 *s, u64 q, u64 n2q)
 {
     u64 d[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = sbuf[(8 * i + col) * DCT_TILE + lane];
-    dct8_pass<8>(d, c, q);
+    dct8_pass<8 * DCT_ROW_INB>(d, c, q, n2q);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) out[(size_t)(8 * i + col) * ct_stride + lane] = shoup_lazy(d[i], s[i], q);
+    for (int i = 0; i < 8; ++i) out[(size_t)(8 * i + col) * ct_stride + lane] = mulc(d[i], s[i], n2q);
 }
 
 }  // namespace fhe

@@ -32,8 +32,14 @@ struct RingDev {
 // =============================================================================================
 // NTT kernels: one CTA per limb-polynomial, n/E threads (csrc/ntt.cuh)
 // =============================================================================================
-template <int LOGN, int LOGE, class RC, bool OUT_FULL>
-__global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_ntt_fwd(const u64 *in, u64 *out, RingDev R)
+// resident CTAs per SM the register allocation is held to: 16 coefficients per thread fit 64
+// registers (1024 threads per SM), 32 coefficients per thread need 128 (512 threads per SM)
+#ifndef FHE_NTT_OCC_THREADS
+#define FHE_NTT_OCC_THREADS 1024
+#endif
+#define NTT_MIN_CTAS(LOGN, LOGE) ((((LOGE) == 4 ? FHE_NTT_OCC_THREADS : 512) >> ((LOGN) - (LOGE))) > 0 ? (((LOGE) == 4 ? FHE_NTT_OCC_THREADS : 512) >> ((LOGN) - (LOGE))) : 1)
+template <int LOGN, int LOGE, int OUT>
+__global__ void __launch_bounds__(1 << (LOGN - LOGE), NTT_MIN_CTAS(LOGN, LOGE)) k_ntt_fwd(const u64 *in, u64 *out, RingDev R)
 {
     using S = NttShape<LOGN, LOGE>;
     static_assert(S::NPASS == 3, "pass chain written for 3 passes");
@@ -44,15 +50,15 @@ __global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_ntt_fwd(const u64 *in, u
     u64 *gout = out + p * S::N;
     const W2 *tw = R.tw + (size_t)j * S::N;
     const LimbDev lp = R.limb[j];
-    ntt_fwd_pass<LOGN, LOGE, 0, RC, OUT_FULL>(tau, gin, gout, smem, tw, lp);
+    ntt_fwd_pass<LOGN, LOGE, 0, OUT>(tau, gin, gout, smem, tw, lp);
     __syncthreads();
-    ntt_fwd_pass<LOGN, LOGE, 1, RC, OUT_FULL>(tau, gin, gout, smem, tw, lp);
+    ntt_fwd_pass<LOGN, LOGE, 1, OUT>(tau, gin, gout, smem, tw, lp);
     __syncthreads();
-    ntt_fwd_pass<LOGN, LOGE, 2, RC, OUT_FULL>(tau, gin, gout, smem, tw, lp);
+    ntt_fwd_pass<LOGN, LOGE, 2, OUT>(tau, gin, gout, smem, tw, lp);
 }
 
-template <int LOGN, int LOGE, class RC>
-__global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_ntt_inv(const u64 *in, u64 *out, RingDev R)
+template <int LOGN, int LOGE, bool SCALE>
+__global__ void __launch_bounds__(1 << (LOGN - LOGE), NTT_MIN_CTAS(LOGN, LOGE)) k_ntt_inv(const u64 *in, u64 *out, RingDev R)
 {
     using S = NttShape<LOGN, LOGE>;
     static_assert(S::NPASS == 3, "pass chain written for 3 passes");
@@ -63,17 +69,17 @@ __global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_ntt_inv(const u64 *in, u
     u64 *gout = out + p * S::N;
     const W2 *itw = R.itw + (size_t)j * S::N;
     const LimbDev lp = R.limb[j];
-    ntt_inv_pass<LOGN, LOGE, 2, RC>(tau, gin, gout, smem, itw, lp);
+    ntt_inv_pass<LOGN, LOGE, 2, SCALE>(tau, gin, gout, smem, itw, lp);
     __syncthreads();
-    ntt_inv_pass<LOGN, LOGE, 1, RC>(tau, gin, gout, smem, itw, lp);
+    ntt_inv_pass<LOGN, LOGE, 1, SCALE>(tau, gin, gout, smem, itw, lp);
     __syncthreads();
-    ntt_inv_pass<LOGN, LOGE, 0, RC>(tau, gin, gout, smem, itw, lp);
+    ntt_inv_pass<LOGN, LOGE, 0, SCALE>(tau, gin, gout, smem, itw, lp);
 }
 
 // Evaluator::multiply_plain as ONE kernel per limb-poly: forward NTT (lazy), dyadic product with
-// the pre-transformed plaintext (Shoup), inverse NTT -- the polynomial is read from HBM once and
-// written once; the NTT-domain values never leave the SM.
-template <int LOGN, int LOGE, class RC>
+// the pre-transformed plaintext (times n^-1), inverse NTT -- the polynomial is read from HBM once
+// and written once; the NTT-domain values never leave the SM.
+template <int LOGN, int LOGE>
 __global__ void __launch_bounds__(1 << (LOGN - LOGE))
 k_mulplain(const u64 *in, u64 *out, const W2 *__restrict__ table, RingDev R)
 {
@@ -87,21 +93,21 @@ k_mulplain(const u64 *in, u64 *out, const W2 *__restrict__ table, RingDev R)
     const W2 *tw = R.tw + (size_t)j * S::N, *itw = R.itw + (size_t)j * S::N;
     const W2 *tab = table + (size_t)j * S::N;
     const LimbDev lp = R.limb[j];
-    ntt_fwd_pass<LOGN, LOGE, 0, RC, false>(tau, gin, gout, smem, tw, lp);
+    ntt_fwd_pass<LOGN, LOGE, 0, NTT_OUT_LAZY>(tau, gin, gout, smem, tw, lp);
     __syncthreads();
-    ntt_fwd_pass<LOGN, LOGE, 1, RC, false>(tau, gin, gout, smem, tw, lp);
+    ntt_fwd_pass<LOGN, LOGE, 1, NTT_OUT_LAZY>(tau, gin, gout, smem, tw, lp);
     __syncthreads();
     u64 v[S::E];
     ntt_fwd_load<LOGN, LOGE, 2>(v, tau, gin, smem);
-    ntt_fwd_compute<LOGN, LOGE, 2, RC>(v, tau, tw, lp);
+    ntt_fwd_compute<LOGN, LOGE, 2>(v, tau, tw, lp);
 #pragma unroll
-    for (int e = 0; e < S::E; ++e) v[e] = shoup_lazy(v[e], tab[e * S::T + tau], lp.q);
-    ntt_inv_compute<LOGN, LOGE, 2, RC>(v, tau, itw, lp);
+    for (int e = 0; e < S::E; ++e) v[e] = mulc(v[e], tab[e * S::T + tau], lp.a.n2q);
+    ntt_inv_compute<LOGN, LOGE, 2, false>(v, tau, itw, lp);
     ntt_inv_store<LOGN, LOGE, 2>(v, tau, gout, smem);
     __syncthreads();
-    ntt_inv_pass<LOGN, LOGE, 1, RC>(tau, gin, gout, smem, itw, lp);
+    ntt_inv_pass<LOGN, LOGE, 1, false>(tau, gin, gout, smem, itw, lp);
     __syncthreads();
-    ntt_inv_pass<LOGN, LOGE, 0, RC>(tau, gin, gout, smem, itw, lp);
+    ntt_inv_pass<LOGN, LOGE, 0, false>(tau, gin, gout, smem, itw, lp);
 }
 
 // =============================================================================================
@@ -120,7 +126,7 @@ k_dct_pointwise(u64 *data, const W2 *__restrict__ ctab, const W2 *__restrict__ s
     const uint32_t tile = blockIdx.x % tiles, j = (blockIdx.x / tiles) % k;
     const unsigned long long ug = blockIdx.x / (tiles * k);
     const size_t pos = (size_t)tile * DCT_TILE + lane;
-    const u64 q = R.limb[j].q;
+    const u64 q = R.limb[j].a.q, n2q = R.limb[j].a.n2q;
     W2 c[DCT_NCONST], s[8];
 #pragma unroll
     for (int i = 0; i < DCT_NCONST; ++i) c[i] = ctab[((size_t)i * k + j) * n + pos];
@@ -134,9 +140,9 @@ k_dct_pointwise(u64 *data, const W2 *__restrict__ ctab, const W2 *__restrict__ s
         const uint32_t poly = (uint32_t)(u & 1);
         u64 *base = data + blk * 64 * ct_stride + ((size_t)poly * k + j) * n + (size_t)tile * DCT_TILE;
         u64 *sb = sbuf[it & 1];
-        dct_row_phase(w, lane, base, ct_stride, sb, c, q);
+        dct_row_phase(w, lane, base, ct_stride, sb, c, q, n2q);
         __syncthreads();
-        dct_col_phase(w, lane, base, ct_stride, sb, c, s, q);
+        dct_col_phase(w, lane, base, ct_stride, sb, c, s, q, n2q);
     }
 }
 
@@ -149,7 +155,7 @@ __global__ void k_elementwise(u64 *a, const u64 *b, unsigned long long total, Ri
 {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        const u64 q = R.limb[(i >> R.logn) % R.k].q;
+        const u64 q = R.limb[(i >> R.logn) % R.k].a.q;
         u64 x = a[i];
         if (OP == 0) x = addmod(x, b[i], q);
         else if (OP == 1) x = submod(x, b[i], q);
@@ -166,7 +172,7 @@ __global__ void k_plain_lift(const u64 *plain, u64 *out, unsigned long long tota
         const uint32_t c = (uint32_t)(i & (R.n - 1)), j = (uint32_t)((i >> R.logn) % R.k);
         const unsigned long long pl = (i >> R.logn) / R.k;
         const u64 m = plain[pl * R.n + c];
-        out[i] = m >= R.plain_thr ? m + (R.limb[j].q - R.t) : m;
+        out[i] = m >= R.plain_thr ? m + (R.limb[j].a.q - R.t) : m;
     }
 }
 // Delta-scaling of plaintexts (Encryptor::preencrypt): [count][n] -> [count][k][n]
@@ -183,22 +189,24 @@ __global__ void k_plain_scale(const u64 *plain, u64 *out, unsigned long long tot
             hi += (s < lo);
             lo = s;
         }
-        out[i] = barrett128(lo, hi, R.limb[j].q, R.ratio0[j], R.ratio1[j]);
+        out[i] = barrett128(lo, hi, R.limb[j].a.q, R.ratio0[j], R.ratio1[j]);
     }
 }
-// w -> (w, floor(w 2^64 / q)); optional second factor: w = a*b mod q first
+// w -> (w, floor(w 2^63 / q)), the mulc constant form; optional second factor (w = a*b mod q
+// first) and optional factor n^-1 (tables that feed an inverse NTT without its own scaling)
 __global__ void k_make_shoup(const u64 *a, const u64 *b, W2 *out, unsigned long long total,
-                             unsigned long long b_period, RingDev R)
+                             unsigned long long b_period, int times_ninv, RingDev R)
 {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const uint32_t j = (uint32_t)((i >> R.logn) % R.k);
-        const u64 q = R.limb[j].q;
+        const u64 q = R.limb[j].a.q;
         u64 w = a[i];
         if (b) w = mulmod_barrett(w, b[i % b_period], q, R.ratio0[j], R.ratio1[j]);
+        if (times_ninv) w = mulmod_barrett(w, R.limb[j].ninv.w, q, R.ratio0[j], R.ratio1[j]);
         W2 r;
         r.w = w;
-        r.wp = (u64)((((unsigned __int128)w) << 64) / q);
+        r.p = (u64)((((unsigned __int128)w) << 63) / q);
         out[i] = r;
     }
 }
@@ -211,7 +219,7 @@ __global__ void k_plain_addsub(u64 *a, const u64 *scaled /*[k][n]*/, unsigned lo
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long ct = i / per, r = i % per;
-        const u64 q = R.limb[r >> R.logn].q;
+        const u64 q = R.limb[r >> R.logn].a.q;
         u64 *p = a + ct * per * size + r;
         *p = SIGN > 0 ? addmod(*p, scaled[r], q) : submod(*p, scaled[r], q);
     }
@@ -225,7 +233,7 @@ __global__ void k_fill_uniform(u64 *dst, unsigned long long first_ct, unsigned l
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const u64 g = first_ct * per_ct + i;  // global element index
-        const u64 q = R.limb[(g >> R.logn) % R.k].q;
+        const u64 q = R.limb[(g >> R.logn) % R.k].a.q;
         dst[i] = mulhi_u64(splitmix64(seed + g * 0x9E3779B97F4A7C15ull), q);
     }
 }
@@ -322,59 +330,65 @@ static int set_smem(K kernel, size_t bytes)
     default: return fail(FHE_ERR_UNSUPPORTED, "unsupported ring degree"); \
     }
 
-template <int LOGN, int LOGE, class RC>
-static int launch_fwd(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, bool full, cudaStream_t st)
+template <int LOGN, int LOGE, int OUT>
+static int launch_fwd_mode(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, cudaStream_t st)
 {
     using S = NttShape<LOGN, LOGE>;
     const size_t smem = S::SMEM_WORDS * sizeof(u64);
-    if (full) {
-        if (int rc = set_smem(k_ntt_fwd<LOGN, LOGE, RC, true>, smem)) return rc;
-        k_ntt_fwd<LOGN, LOGE, RC, true><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
-    } else {
-        if (int rc = set_smem(k_ntt_fwd<LOGN, LOGE, RC, false>, smem)) return rc;
-        k_ntt_fwd<LOGN, LOGE, RC, false><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
-    }
+    if (int rc = set_smem(k_ntt_fwd<LOGN, LOGE, OUT>, smem)) return rc;
+    k_ntt_fwd<LOGN, LOGE, OUT><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
     c->launches++;
     CU_TRY(cudaGetLastError());
     return FHE_OK;
 }
-template <int LOGN, int LOGE, class RC>
+template <int LOGN, int LOGE>
+static int launch_fwd(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, int mode, cudaStream_t st)
+{
+    if (mode == NTT_OUT_CANON) return launch_fwd_mode<LOGN, LOGE, NTT_OUT_CANON>(c, in, out, npoly, st);
+    return launch_fwd_mode<LOGN, LOGE, NTT_OUT_REDUCED>(c, in, out, npoly, st);
+}
+template <int LOGN, int LOGE, bool SCALE>
 static int launch_inv(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, cudaStream_t st)
 {
     using S = NttShape<LOGN, LOGE>;
     const size_t smem = S::SMEM_WORDS * sizeof(u64);
-    if (int rc = set_smem(k_ntt_inv<LOGN, LOGE, RC>, smem)) return rc;
-    k_ntt_inv<LOGN, LOGE, RC><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
+    if (int rc = set_smem(k_ntt_inv<LOGN, LOGE, SCALE>, smem)) return rc;
+    k_ntt_inv<LOGN, LOGE, SCALE><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
     c->launches++;
     CU_TRY(cudaGetLastError());
     return FHE_OK;
 }
-template <int LOGN, int LOGE, class RC>
+template <int LOGN, int LOGE>
 static int launch_mulplain(fhe_ctx *c, const u64 *in, u64 *out, const W2 *tab, uint64_t npoly, cudaStream_t st)
 {
     using S = NttShape<LOGN, LOGE>;
     const size_t smem = S::SMEM_WORDS * sizeof(u64);
-    if (int rc = set_smem(k_mulplain<LOGN, LOGE, RC>, smem)) return rc;
-    k_mulplain<LOGN, LOGE, RC><<<(unsigned)npoly, S::T, smem, st>>>(in, out, tab, c->dev);
+    if (int rc = set_smem(k_mulplain<LOGN, LOGE>, smem)) return rc;
+    k_mulplain<LOGN, LOGE><<<(unsigned)npoly, S::T, smem, st>>>(in, out, tab, c->dev);
     c->launches++;
     CU_TRY(cudaGetLastError());
     return FHE_OK;
 }
 
-static int ntt_forward(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, bool full, cudaStream_t st)
+// mode: NTT_OUT_CANON ([0, q), the public transform and the plaintext tables) or
+// NTT_OUT_REDUCED ([0, 4q), input range of the pointwise DCT kernel)
+static int ntt_forward(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, int mode, cudaStream_t st)
 {
     if (!npoly) return FHE_OK;
     if (npoly > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many polynomials in one call");
-#define CALL(LN, LE) return launch_fwd<LN, LE, RangeA>(c, in, out, npoly, full, st)
+#define CALL(LN, LE) return launch_fwd<LN, LE>(c, in, out, npoly, mode, st)
     FHE_DISPATCH_LOGN(c->host.logn, CALL)
 #undef CALL
     return FHE_OK;
 }
-static int ntt_inverse(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, cudaStream_t st)
+// scale: multiply by n^-1 (public transform) or not (the preceding table already carries n^-1)
+static int ntt_inverse(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, bool scale, cudaStream_t st)
 {
     if (!npoly) return FHE_OK;
     if (npoly > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many polynomials in one call");
-#define CALL(LN, LE) return launch_inv<LN, LE, RangeA>(c, in, out, npoly, st)
+#define CALL(LN, LE)                                                        \
+    if (scale) return launch_inv<LN, LE, true>(c, in, out, npoly, st);      \
+    return launch_inv<LN, LE, false>(c, in, out, npoly, st)
     FHE_DISPATCH_LOGN(c->host.logn, CALL)
 #undef CALL
     return FHE_OK;
@@ -421,8 +435,7 @@ int fhe_ctx_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, int de
     auto c = std::make_unique<fhe_ctx>();
     std::string err;
     if (!build_ring(c->host, n, k, q, t, err)) return fail(FHE_ERR_INVALID_ARGUMENT, err);
-    if (c->host.max_qbits > 57)
-        return fail(FHE_ERR_UNSUPPORTED, "coeff_modulus primes above 57 bits are not enabled in this build");
+    if (!c->host.unsupported.empty()) return fail(FHE_ERR_UNSUPPORTED, c->host.unsupported);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -620,19 +633,19 @@ int fhe_ntt_forward(fhe_ctx *c, uint64_t *a, uint64_t npoly)
 {
     if (int rc = check_ctx(c)) return rc;
     if (!a) return fail(FHE_ERR_INVALID_ARGUMENT, "null buffer");
-    return ntt_forward(c, (const u64 *)a, (u64 *)a, npoly, true, c->stream);
+    return ntt_forward(c, (const u64 *)a, (u64 *)a, npoly, NTT_OUT_CANON, c->stream);
 }
 int fhe_ntt_inverse(fhe_ctx *c, uint64_t *a, uint64_t npoly)
 {
     if (int rc = check_ctx(c)) return rc;
     if (!a) return fail(FHE_ERR_INVALID_ARGUMENT, "null buffer");
-    return ntt_inverse(c, (const u64 *)a, (u64 *)a, npoly, c->stream);
+    return ntt_inverse(c, (const u64 *)a, (u64 *)a, npoly, true, c->stream);
 }
 
 // plaintexts (host [count][n]) -> device W2 table [count][k][n] of NTT(lift(plain)) (optionally
 // times a second table, period b_period) and, if d_scaled, the Delta-scaled polys.
-static int build_plain_tables(fhe_ctx *c, const uint64_t *plain, uint32_t count, W2 *d_ntt, u64 *d_scaled,
-                              u64 *d_values_out /* optional [count][k][n] reduced NTT values */)
+static int build_plain_tables(fhe_ctx *c, const uint64_t *plain, uint32_t count, W2 *d_ntt, int ntt_times_ninv,
+                              u64 *d_scaled, u64 *d_values_out /* optional [count][k][n] reduced NTT values */)
 {
     const uint32_t n = c->host.n, k = c->host.k;
     for (size_t i = 0; i < (size_t)count * n; ++i)
@@ -649,8 +662,8 @@ static int build_plain_tables(fhe_ctx *c, const uint64_t *plain, uint32_t count,
         if (d_scaled) { k_plain_scale<<<g, 256, 0, c->stream>>>(d_plain, d_scaled, total, c->dev); c->launches++; }
         k_plain_lift<<<g, 256, 0, c->stream>>>(d_plain, d_lift, total, c->dev);
         c->launches++;
-        if ((rc = ntt_forward(c, d_lift, d_lift, (uint64_t)count * k, true, c->stream))) break;
-        if (d_ntt) { k_make_shoup<<<g, 256, 0, c->stream>>>(d_lift, nullptr, d_ntt, total, 1, c->dev); c->launches++; }
+        if ((rc = ntt_forward(c, d_lift, d_lift, (uint64_t)count * k, NTT_OUT_CANON, c->stream))) break;
+        if (d_ntt) { k_make_shoup<<<g, 256, 0, c->stream>>>(d_lift, nullptr, d_ntt, total, 1, ntt_times_ninv, c->dev); c->launches++; }
         if (d_values_out && cudaMemcpyAsync(d_values_out, d_lift, total * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { rc = fail(FHE_ERR_CUDA, "table copy failed"); break; }
         if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = fail(FHE_ERR_CUDA, "plaintext table kernels failed"); break; }
     } while (0);
@@ -676,7 +689,7 @@ int fhe_ptab_create(fhe_ctx *c, const uint64_t *plain, uint32_t count, fhe_ptab 
     CU_TRY(cudaMalloc(&t->d_ntt, total * sizeof(W2)));
     cudaError_t e = cudaMalloc(&t->d_scaled, total * sizeof(u64));
     if (e != cudaSuccess) { cudaFree(t->d_ntt); return fail(FHE_ERR_ALLOC, "cudaMalloc failed"); }
-    if (int rc = build_plain_tables(c, plain, count, t->d_ntt, t->d_scaled, nullptr)) {
+    if (int rc = build_plain_tables(c, plain, count, t->d_ntt, 1, t->d_scaled, nullptr)) {
         cudaFree(t->d_ntt); cudaFree(t->d_scaled);
         return rc;
     }
@@ -701,7 +714,7 @@ int fhe_multiply_plain(fhe_ctx *c, uint64_t *a, uint64_t n_ct, uint32_t size, co
     if (!npoly) return FHE_OK;
     if (npoly > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many polynomials in one call");
     const W2 *table = tab->d_ntt + (size_t)index * c->host.k * c->host.n;
-#define CALL(LN, LE) return launch_mulplain<LN, LE, RangeA>(c, (const u64 *)a, (u64 *)a, table, npoly, c->stream)
+#define CALL(LN, LE) return launch_mulplain<LN, LE>(c, (const u64 *)a, (u64 *)a, table, npoly, c->stream)
     FHE_DISPATCH_LOGN(c->host.logn, CALL)
 #undef CALL
     return FHE_OK;
@@ -744,19 +757,20 @@ int fhe_dct_plan_create(fhe_ctx *c, const uint64_t *dct_consts, const uint64_t *
     CU_TRY(cudaMalloc(&p->d_s, 64 * per * sizeof(W2)));
     CU_TRY(cudaMalloc(&d_e, per * sizeof(u64)));
     CU_TRY(cudaMalloc(&d_q, 64 * per * sizeof(u64)));
-    int rc = build_plain_tables(c, dct_consts, DCT_NCONST, p->d_c, nullptr, nullptr);
-    if (!rc) rc = build_plain_tables(c, eighth, 1, nullptr, nullptr, d_e);
-    if (!rc && quant) rc = build_plain_tables(c, quant, 64, nullptr, nullptr, d_q);
+    int rc = build_plain_tables(c, dct_consts, DCT_NCONST, p->d_c, 0, nullptr, nullptr);
+    if (!rc) rc = build_plain_tables(c, eighth, 1, nullptr, 0, nullptr, d_e);
+    if (!rc && quant) rc = build_plain_tables(c, quant, 64, nullptr, 0, nullptr, d_q);
     if (!rc) {
         // merged scale constants: s[i] = NTT(0.125) * NTT(1/quant[i]) (ring multiplication is
-        // associative, so (x * 0.125) * (1/quant) == x * (0.125 * 1/quant) exactly), or NTT(0.125).
+        // associative, so (x * 0.125) * (1/quant) == x * (0.125 * 1/quant) exactly), or NTT(0.125);
+        // times n^-1, which the inverse NTT after the pointwise kernel then does not apply again.
         const unsigned long long total = 64ull * per;
         const int g = grid_for(total, 256, c->sm_count);
-        if (quant) k_make_shoup<<<g, 256, 0, c->stream>>>(d_q, d_e, p->d_s, total, per, c->dev);
+        if (quant) k_make_shoup<<<g, 256, 0, c->stream>>>(d_q, d_e, p->d_s, total, per, 1, c->dev);
         else {
             // replicate the eighth table 64 times
             for (int i = 0; i < 64; ++i) cudaMemcpyAsync(d_q + (size_t)i * per, d_e, per * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream);
-            k_make_shoup<<<g, 256, 0, c->stream>>>(d_q, nullptr, p->d_s, total, 1, c->dev);
+            k_make_shoup<<<g, 256, 0, c->stream>>>(d_q, nullptr, p->d_s, total, 1, 1, c->dev);
         }
         c->launches++;
         if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = fail(FHE_ERR_CUDA, "scale table kernel failed");
@@ -790,7 +804,7 @@ static int dct_chunk(fhe_ctx *c, const fhe_dct_plan *plan, const u64 *in, u64 *o
         return FHE_OK;
     };
     if (int rc = mark()) return rc;
-    if (int rc = ntt_forward(c, in, out, npoly, true, st)) return rc;
+    if (int rc = ntt_forward(c, in, out, npoly, NTT_OUT_REDUCED, st)) return rc;
     if (int rc = mark()) return rc;
     const unsigned long long nunits = nblocks * 2;
     const int upc = 16;
@@ -801,7 +815,7 @@ static int dct_chunk(fhe_ctx *c, const fhe_dct_plan *plan, const u64 *in, u64 *o
     c->launches++;
     CU_TRY(cudaGetLastError());
     if (int rc = mark()) return rc;
-    if (int rc = ntt_inverse(c, out, out, npoly, st)) return rc;
+    if (int rc = ntt_inverse(c, out, out, npoly, false, st)) return rc;
     return mark();
 }
 

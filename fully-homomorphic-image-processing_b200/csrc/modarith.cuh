@@ -1,13 +1,24 @@
-// modarith.cuh -- 64-bit modular arithmetic over the RNS limbs (q_j < 2^62).
+// modarith.cuh -- 64-bit modular arithmetic over the RNS limbs (q_j < 2^55).
 //
 // B200 replacement for SEAL 2.3's util/uintarithsmallmod (Barrett) and the Harvey/Shoup lazy
 // multiplication inside util/smallntt (both [SEAL-recall], sources absent).
-// Every function is __host__ __device__ so the exact kernel bodies can also be executed
-// thread-by-thread on the CPU by tests/emu (index math is checked here, where there is no GPU).
+//
+// Cost model measured on B200 (profiles/r01_*): the FMA pipe issues a 32-bit IMAD per cycle per
+// SM sub-partition and an IMAD.WIDE / IMAD.HI every 2 cycles; the ALU pipe (IADD3, SEL, SHF,
+// ISETP) issues every 2 cycles.  A textbook Shoup multiplication (exact mul.hi.u64 + two
+// mul.lo.u64) is 17 SASS instructions.  `mulc` below is 11: the quotient estimate drops the
+// low x low partial product and keeps the carries out of the critical path by scaling the
+// companion constant with 2^63 instead of 2^64, at the price of a wider lazy range [0, 5q).
+// All lazy ranges are tracked at compile time by the callers (ntt.cuh, dct.cuh); every value
+// handed back to the user is canonical ([0, q)), so results are bit-identical to SEAL's.
+//
+// Every function is __host__ __device__ with one arithmetic definition (the device path only
+// spells the same operations as PTX), so tests/emu executes the exact kernel bodies on the CPU.
 #pragma once
 #include <cstdint>
 
 typedef unsigned long long u64;
+typedef unsigned int u32;
 
 #if defined(__CUDACC__)
 #define FHE_HD __host__ __device__ __forceinline__
@@ -15,8 +26,19 @@ typedef unsigned long long u64;
 #define FHE_HD inline
 #endif
 
-struct W2 {  // twiddle / constant with its Shoup companion floor(w * 2^64 / q)
-    u64 w, wp;
+// A multiplier constant w in [0, q) with its companion p = floor(w * 2^63 / q) < 2^63.
+struct alignas(16) W2 {
+    u64 w, p;
+};
+
+// Per-limb constants of the lazy arithmetic.
+struct LimbArith {
+    u64 q;     // the prime, < 2^55
+    u64 n2q;   // -2q mod 2^64
+    u64 nq;    // -q mod 2^64
+    u64 q5;    // 5q: offset that keeps  x + q5 - mulc(..)  non-negative
+    u32 mu63;  // floor(2^63 / q): quotient estimate of reduce63
+    u32 mu64;  // floor(2^64 / q): quotient estimate of canon
 };
 
 FHE_HD u64 mulhi_u64(u64 a, u64 b)
@@ -27,21 +49,80 @@ FHE_HD u64 mulhi_u64(u64 a, u64 b)
     return (u64)(((unsigned __int128)a * b) >> 64);
 #endif
 }
+FHE_HD u32 mulhi_u32(u32 a, u32 b)
+{
+#if defined(__CUDA_ARCH__)
+    return __umulhi(a, b);
+#else
+    return (u32)(((u64)a * b) >> 32);
+#endif
+}
 
-FHE_HD u64 umin_u64(u64 a, u64 b) { return a < b ? a : b; }
+// x * c.w - Q * 2q  with  Q = x1*p1 + floor((x0*p1 + x1*p0) / 2^32)  (x = x1:x0, p = p1:p0).
+// Requires x < 2^63, c.w < q < 2^55.  Q is within 2.5 below x*w/(2q) and never above it, so the
+// result is congruent to x*w mod q and lies in [0, 5q).  x0*p1 + x1*p0 < 2^64 because both p
+// and x are below 2^63: there is no carry to propagate.
+FHE_HD u64 mulc(u64 x, W2 c, u64 n2q)
+{
+    const u32 x0 = (u32)x, x1 = (u32)(x >> 32), w0 = (u32)c.w, w1 = (u32)(c.w >> 32);
+    const u32 p0 = (u32)c.p, p1 = (u32)(c.p >> 32), n0 = (u32)n2q, n1 = (u32)(n2q >> 32);
+#if defined(__CUDA_ARCH__)
+    u64 r;
+    asm("{\n\t"
+        ".reg .u32 h, z, q0, q1, lo, hi;\n\t"
+        ".reg .u64 t, H, Q, acc;\n\t"
+        "mul.wide.u32 t, %2, %5;\n\t"          // x1*p0
+        "mad.wide.u32 t, %1, %6, t;\n\t"       // + x0*p1
+        "mov.b64 {z, h}, t;\n\t"
+        "cvt.u64.u32 H, h;\n\t"
+        "mad.wide.u32 Q, %2, %6, H;\n\t"       // Q = x1*p1 + h
+        "mov.b64 {q0, q1}, Q;\n\t"
+        "mul.wide.u32 acc, %1, %3;\n\t"        // x0*w0
+        "mad.wide.u32 acc, q0, %7, acc;\n\t"   // + Q0*n0
+        "mov.b64 {lo, hi}, acc;\n\t"
+        "mad.lo.u32 hi, %1, %4, hi;\n\t"       // + 2^32 (x0*w1 + x1*w0 + Q0*n1 + Q1*n0)
+        "mad.lo.u32 hi, %2, %3, hi;\n\t"
+        "mad.lo.u32 hi, q0, %8, hi;\n\t"
+        "mad.lo.u32 hi, q1, %7, hi;\n\t"
+        "mov.b64 %0, {lo, hi};\n\t"
+        "}"
+        : "=l"(r)
+        : "r"(x0), "r"(x1), "r"(w0), "r"(w1), "r"(p0), "r"(p1), "r"(n0), "r"(n1));
+    return r;
+#else
+    const u64 t = (u64)x0 * p1 + (u64)x1 * p0;
+    const u64 Q = (u64)x1 * p1 + (t >> 32);
+    return x * c.w + Q * n2q;
+#endif
+}
 
-// x * w mod q, result in [0, 2q), valid for ANY 64-bit x (w < q, wp = floor(w 2^64 / q)).
-FHE_HD u64 shoup_lazy(u64 x, u64 w, u64 wp, u64 q) { return x * w - mulhi_u64(x, wp) * q; }
-FHE_HD u64 shoup_lazy(u64 x, W2 c, u64 q) { return shoup_lazy(x, c.w, c.wp, q); }
+// x < 2^63  ->  congruent value in [0, 4q):  x - Q*2q with Q = floor(x1 * mu63 / 2^32), which
+// is floor(x/(2q)) or one less (mu63 = floor(2^63/q) < 2^32 because q > 2^31).
+FHE_HD u64 reduce63(u64 x, const LimbArith &L)
+{
+    const u32 Q = mulhi_u32((u32)(x >> 32), L.mu63);
+    return x + (u64)Q * L.n2q;  // Q < 2^32: IMAD.WIDE + IMAD
+}
 
-// x in [0, 2m) -> [0, m)   (x - m wraps to a huge value when x < m, min picks x)
-FHE_HD u64 csub(u64 x, u64 m) { return umin_u64(x, x - m); }
+// x in [0, 2m) -> [0, m), for m < 2^63 (the sign bit of x - m says which)
+FHE_HD u64 csub(u64 x, u64 m)
+{
+    const u64 t = x - m;
+    return (long long)t < 0 ? x : t;
+}
+
+// x < 2^63  ->  x mod q, canonical.  k = floor(x1 * mu64 / 2^32) is floor(x/q) or one less.
+FHE_HD u64 canon(u64 x, const LimbArith &L)
+{
+    const u32 k = mulhi_u32((u32)(x >> 32), L.mu64);
+    return csub(x + (u64)k * L.nq, L.q);
+}
 
 FHE_HD u64 addmod(u64 a, u64 b, u64 q) { return csub(a + b, q); }
 FHE_HD u64 submod(u64 a, u64 b, u64 q) { return csub(a - b + q, q); }
 FHE_HD u64 negmod(u64 a, u64 q) { return a ? q - a : 0; }
 
-// Barrett 128 -> 64 with ratio = floor(2^128 / q) = (r1:r0); result in [0, q).
+// Barrett 128 -> 64 with ratio = floor(2^128 / q) = (r1:r0); result in [0, q).  Table setup only.
 FHE_HD u64 barrett128(u64 z0, u64 z1, u64 q, u64 r0, u64 r1)
 {
     u64 t0h = mulhi_u64(z0, r0);

@@ -18,7 +18,8 @@ typedef unsigned __int128 u128;
 
 struct HostLimb {
     u64 q = 0, psi = 0, ratio0 = 0, ratio1 = 0, delta = 0;
-    std::vector<W2> tw, itw;  // [n], index m+i as in SEAL's root-power tables
+    std::vector<W2> tw, itw;  // [n], per-pass layout (ntt.cuh PassGeom::tw_index); n-1 entries used
+    u64 itw1 = 0;             // psi^-(n/2): SEAL-order inverse table entry 1
     LimbDev dev{};
 };
 
@@ -26,6 +27,7 @@ struct HostRing {
     uint32_t n = 0, logn = 0, k = 0;
     u64 t = 0, q_mod_t = 0, plain_thr = 0;
     int max_qbits = 0;
+    std::string unsupported;  // non-empty: valid SEAL parameters this build's lazy arithmetic cannot run
     std::vector<HostLimb> limbs;
 };
 
@@ -39,7 +41,16 @@ inline u64 h_powmod(u64 b, u64 e, u64 q)
     return r;
 }
 inline u64 h_invmod(u64 a, u64 q) { return h_powmod(a, q - 2, q); }
-inline W2 h_shoup(u64 w, u64 q) { return W2{w, (u64)((((u128)w) << 64) / q)}; }
+// multiplier constant with its mulc companion floor(w 2^63 / q)  (modarith.cuh)
+inline W2 h_shoup(u64 w, u64 q) { return W2{w, (u64)((((u128)w) << 63) / q)}; }
+inline LimbArith h_limb_arith(u64 q)
+{
+    LimbArith a;
+    a.q = q; a.n2q = 0 - 2 * q; a.nq = 0 - q; a.q5 = 5 * q;
+    a.mu63 = (u32)((((u128)1) << 63) / q);
+    a.mu64 = (u32)((((u128)1) << 64) / q);
+    return a;
+}
 
 inline bool h_is_prime(u64 n)
 {
@@ -99,6 +110,8 @@ inline bool build_ring(HostRing &R, uint32_t n, uint32_t k, const uint64_t *q, u
         HostLimb &L = R.limbs[j];
         u64 qj = q[j];
         if (qj >> 61) { err = "coeff_modulus primes must be below 2^61"; return false; }
+        if (qj >> 55) { R.unsupported = "coeff_modulus primes of 55 bits or fewer are supported by this build (SEAL 2.3 coeff_modulus_128 uses 54/55-bit primes)"; }
+        if (qj >> 40 == 0) { R.unsupported = "coeff_modulus primes below 2^40 are not supported by this build"; }
         if (qj <= t) { err = "coeff_modulus primes must exceed plain_modulus"; return false; }
         if ((qj - 1) % (2ull * n)) { err = "coeff_modulus prime is not 1 mod 2n"; return false; }
         if (!h_is_prime(qj)) { err = "coeff_modulus element is not prime"; return false; }
@@ -114,17 +127,26 @@ inline bool build_ring(HostRing &R, uint32_t n, uint32_t k, const uint64_t *q, u
         std::vector<u64> pw(n);
         pw[0] = 1;
         for (uint32_t i = 1; i < n; ++i) pw[i] = h_mulmod(pw[i - 1], L.psi, qj);
-        L.tw.resize(n); L.itw.resize(n);
+        std::vector<W2> seal_tw(n), seal_itw(n);
         for (uint32_t idx = 0; idx < n; ++idx) {
             u64 w = pw[h_bitrev(idx, R.logn)];
-            L.tw[idx] = h_shoup(w, qj);
-            L.itw[idx] = h_shoup(h_invmod(w, qj), qj);
+            seal_tw[idx] = h_shoup(w, qj);
+            seal_itw[idx] = h_shoup(h_invmod(w, qj), qj);
+        }
+        L.tw.assign(n, W2{0, 0}); L.itw.assign(n, W2{0, 0});
+        switch (R.logn) {
+        case 10: ntt_permute_table<10, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<10, 4>(seal_itw.data(), L.itw.data()); break;
+        case 11: ntt_permute_table<11, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<11, 4>(seal_itw.data(), L.itw.data()); break;
+        case 12: ntt_permute_table<12, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<12, 4>(seal_itw.data(), L.itw.data()); break;
+        case 13: ntt_permute_table<13, 5>(seal_tw.data(), L.tw.data()); ntt_permute_table<13, 5>(seal_itw.data(), L.itw.data()); break;
+        case 14: ntt_permute_table<14, 5>(seal_tw.data(), L.tw.data()); ntt_permute_table<14, 5>(seal_itw.data(), L.itw.data()); break;
         }
         u64 ninv = h_invmod(n % qj, qj);
-        L.dev.q = qj;
-        L.dev.one = h_shoup(1, qj);
+        L.itw1 = seal_itw[1].w;
+        L.dev.a = h_limb_arith(qj);
         L.dev.ninv = h_shoup(ninv, qj);
-        L.dev.ninv_w1 = h_shoup(h_mulmod(ninv, L.itw[1].w, qj), qj);
+        L.dev.ninv_w1 = h_shoup(h_mulmod(ninv, L.itw1, qj), qj);
+        L.dev.iw1 = seal_itw[1];
     }
     // q = prod q_j (multi-word), Delta = floor(q/t), q mod t
     std::vector<u64> big(1, 1);

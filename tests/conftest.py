@@ -48,8 +48,13 @@ def emu_lib():
     E.emu_ring_create.restype = C.c_void_p
     E.emu_ring_create.argtypes = [C.c_uint32, C.c_uint32, u64p, C.c_uint64, C.c_char_p, C.c_int]
     E.emu_ring_destroy.argtypes = [C.c_void_p]
-    E.emu_ntt_forward.argtypes = [C.c_void_p, C.c_int, u64p, u64p, C.c_int, C.c_int]
+    E.emu_ntt_forward.argtypes = [C.c_void_p, C.c_int, u64p, u64p, C.c_int]
     E.emu_ntt_inverse.argtypes = [C.c_void_p, C.c_int, u64p, u64p, C.c_int]
+    E.emu_mulc.restype = C.c_uint64
+    E.emu_mulc.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint64]
+    for f in ("emu_reduce63", "emu_canon"):
+        getattr(E, f).restype = C.c_uint64
+        getattr(E, f).argtypes = [C.c_void_p, C.c_int, C.c_uint64]
     E.emu_dct_quant.argtypes = [C.c_void_p, u64p, C.c_uint64, u64p, u64p, u64p]
     for f in ("emu_psi", "emu_delta"):
         getattr(E, f).restype = C.c_uint64

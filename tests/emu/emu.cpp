@@ -19,16 +19,17 @@ using namespace fhe;
 
 template <int V> using ic = std::integral_constant<int, V>;
 
-template <int LOGN, int LOGE, class RC>
-static void emu_fwd(const HostLimb &L, const u64 *in, u64 *out, bool full)
+template <int LOGN, int LOGE>
+static void emu_fwd(const HostLimb &L, const u64 *in, u64 *out, int mode)
 {
     using S = NttShape<LOGN, LOGE>;
     std::vector<u64> smem(S::SMEM_WORDS), tmp(in, in + S::N);
     auto pass = [&](auto tag) {
         constexpr int P = decltype(tag)::value;
         for (int tau = 0; tau < S::T; ++tau) {
-            if (full) ntt_fwd_pass<LOGN, LOGE, P, RC, true>(tau, tmp.data(), out, smem.data(), L.tw.data(), L.dev);
-            else ntt_fwd_pass<LOGN, LOGE, P, RC, false>(tau, tmp.data(), out, smem.data(), L.tw.data(), L.dev);
+            if (mode == NTT_OUT_CANON) ntt_fwd_pass<LOGN, LOGE, P, NTT_OUT_CANON>(tau, tmp.data(), out, smem.data(), L.tw.data(), L.dev);
+            else if (mode == NTT_OUT_REDUCED) ntt_fwd_pass<LOGN, LOGE, P, NTT_OUT_REDUCED>(tau, tmp.data(), out, smem.data(), L.tw.data(), L.dev);
+            else ntt_fwd_pass<LOGN, LOGE, P, NTT_OUT_LAZY>(tau, tmp.data(), out, smem.data(), L.tw.data(), L.dev);
         }
     };
     pass(ic<0>{});
@@ -36,15 +37,17 @@ static void emu_fwd(const HostLimb &L, const u64 *in, u64 *out, bool full)
     if constexpr (S::NPASS > 2) pass(ic<2>{});
     if constexpr (S::NPASS > 3) pass(ic<3>{});
 }
-template <int LOGN, int LOGE, class RC>
-static void emu_inv(const HostLimb &L, const u64 *in, u64 *out)
+template <int LOGN, int LOGE>
+static void emu_inv(const HostLimb &L, const u64 *in, u64 *out, bool scale)
 {
     using S = NttShape<LOGN, LOGE>;
     std::vector<u64> smem(S::SMEM_WORDS), tmp(in, in + S::N);
     auto pass = [&](auto tag) {
         constexpr int P = decltype(tag)::value;
-        for (int tau = 0; tau < S::T; ++tau)
-            ntt_inv_pass<LOGN, LOGE, P, RC>(tau, tmp.data(), out, smem.data(), L.itw.data(), L.dev);
+        for (int tau = 0; tau < S::T; ++tau) {
+            if (scale) ntt_inv_pass<LOGN, LOGE, P, true>(tau, tmp.data(), out, smem.data(), L.itw.data(), L.dev);
+            else ntt_inv_pass<LOGN, LOGE, P, false>(tau, tmp.data(), out, smem.data(), L.itw.data(), L.dev);
+        }
     };
     if constexpr (S::NPASS > 3) pass(ic<3>{});
     if constexpr (S::NPASS > 2) pass(ic<2>{});
@@ -52,29 +55,27 @@ static void emu_inv(const HostLimb &L, const u64 *in, u64 *out)
     pass(ic<0>{});
 }
 
-template <class RC>
-static int fwd_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, bool full)
+static int fwd_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, int mode)
 {
     const HostLimb &L = R.limbs[j];
     switch (R.logn) {
-    case 10: emu_fwd<10, 4, RC>(L, in, out, full); return 0;
-    case 11: emu_fwd<11, 4, RC>(L, in, out, full); return 0;
-    case 12: emu_fwd<12, 4, RC>(L, in, out, full); return 0;
-    case 13: emu_fwd<13, 5, RC>(L, in, out, full); return 0;
-    case 14: emu_fwd<14, 5, RC>(L, in, out, full); return 0;
+    case 10: emu_fwd<10, 4>(L, in, out, mode); return 0;
+    case 11: emu_fwd<11, 4>(L, in, out, mode); return 0;
+    case 12: emu_fwd<12, 4>(L, in, out, mode); return 0;
+    case 13: emu_fwd<13, 5>(L, in, out, mode); return 0;
+    case 14: emu_fwd<14, 5>(L, in, out, mode); return 0;
     default: return -1;
     }
 }
-template <class RC>
-static int inv_dispatch(const HostRing &R, int j, const u64 *in, u64 *out)
+static int inv_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, bool scale)
 {
     const HostLimb &L = R.limbs[j];
     switch (R.logn) {
-    case 10: emu_inv<10, 4, RC>(L, in, out); return 0;
-    case 11: emu_inv<11, 4, RC>(L, in, out); return 0;
-    case 12: emu_inv<12, 4, RC>(L, in, out); return 0;
-    case 13: emu_inv<13, 5, RC>(L, in, out); return 0;
-    case 14: emu_inv<14, 5, RC>(L, in, out); return 0;
+    case 10: emu_inv<10, 4>(L, in, out, scale); return 0;
+    case 11: emu_inv<11, 4>(L, in, out, scale); return 0;
+    case 12: emu_inv<12, 4>(L, in, out, scale); return 0;
+    case 13: emu_inv<13, 5>(L, in, out, scale); return 0;
+    case 14: emu_inv<14, 5>(L, in, out, scale); return 0;
     default: return -1;
     }
 }
@@ -85,7 +86,7 @@ void *emu_ring_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, cha
 {
     auto R = std::make_unique<HostRing>();
     std::string e;
-    if (!build_ring(*R, n, k, q, t, e)) {
+    if (!build_ring(*R, n, k, q, t, e) || !(e = R->unsupported).empty()) {
         if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
         return nullptr;
     }
@@ -96,19 +97,24 @@ uint64_t emu_psi(void *r, int j) { return ((HostRing *)r)->limbs[j].psi; }
 uint64_t emu_delta(void *r, int j) { return ((HostRing *)r)->limbs[j].delta; }
 uint64_t emu_q_mod_t(void *r) { return ((HostRing *)r)->q_mod_t; }
 
-// range_class: 0 = RangeA (q < 2^57), 1 = RangeB (q < 2^61)
-int emu_ntt_forward(void *r, int j, const uint64_t *in, uint64_t *out, int full, int range_class)
+// mode: NTT_OUT_LAZY (0), NTT_OUT_REDUCED (1: [0, 4q)), NTT_OUT_CANON (2: [0, q))
+int emu_ntt_forward(void *r, int j, const uint64_t *in, uint64_t *out, int mode)
 {
-    const HostRing &R = *(HostRing *)r;
-    return range_class ? fwd_dispatch<RangeB>(R, j, (const u64 *)in, (u64 *)out, full)
-                       : fwd_dispatch<RangeA>(R, j, (const u64 *)in, (u64 *)out, full);
+    return fwd_dispatch(*(HostRing *)r, j, (const u64 *)in, (u64 *)out, mode);
 }
-int emu_ntt_inverse(void *r, int j, const uint64_t *in, uint64_t *out, int range_class)
+// input values < 5q; scale != 0 multiplies by n^-1
+int emu_ntt_inverse(void *r, int j, const uint64_t *in, uint64_t *out, int scale)
 {
-    const HostRing &R = *(HostRing *)r;
-    return range_class ? inv_dispatch<RangeB>(R, j, (const u64 *)in, (u64 *)out)
-                       : inv_dispatch<RangeA>(R, j, (const u64 *)in, (u64 *)out);
+    return inv_dispatch(*(HostRing *)r, j, (const u64 *)in, (u64 *)out, scale != 0);
 }
+// x*w lazily (mulc), reduce63 and canon of single values, for range tests
+uint64_t emu_mulc(void *r, int j, uint64_t x, uint64_t w)
+{
+    const HostLimb &L = ((HostRing *)r)->limbs[j];
+    return mulc(x, h_shoup(w, L.q), L.dev.a.n2q);
+}
+uint64_t emu_reduce63(void *r, int j, uint64_t x) { return reduce63(x, ((HostRing *)r)->limbs[j].dev.a); }
+uint64_t emu_canon(void *r, int j, uint64_t x) { return canon(x, ((HostRing *)r)->limbs[j].dev.a); }
 
 // Emulated fused DCT(+quantize) on `nblocks` blocks: forward NTT of every limb-poly, pointwise
 // row/column phases per (unit, limb, tile), inverse NTT.  plains: [12][n] DCT constants,
@@ -123,7 +129,7 @@ int emu_dct_quant(void *r, uint64_t *data_, uint64_t nblocks, const uint64_t *pl
     auto lift_ntt = [&](const uint64_t *plain, uint32_t j, std::vector<u64> &out) {
         out.assign(n, 0);
         for (uint32_t i = 0; i < n; ++i) out[i] = plain[i] >= R.plain_thr ? plain[i] + (R.limbs[j].q - R.t) : plain[i];
-        fwd_dispatch<RangeA>(R, j, out.data(), out.data(), true);
+        fwd_dispatch(R, j, out.data(), out.data(), NTT_OUT_CANON);
     };
     std::vector<std::vector<W2>> ctab(k), stab(k);
     std::vector<u64> a, b;
@@ -139,36 +145,36 @@ int emu_dct_quant(void *r, uint64_t *data_, uint64_t nblocks, const uint64_t *pl
         for (int s = 0; s < 64; ++s) {
             if (quant) lift_ntt(quant + (size_t)s * n, j, b);
             for (uint32_t i = 0; i < n; ++i)
-                stab[j][(size_t)s * n + i] = h_shoup(quant ? h_mulmod(a[i], b[i], q) : a[i], q);
+                stab[j][(size_t)s * n + i] = h_shoup(h_mulmod(quant ? h_mulmod(a[i], b[i], q) : a[i], R.limbs[j].dev.ninv.w, q), q);
         }
     }
     const size_t ct_stride = (size_t)2 * k * n;
     for (uint64_t blk = 0; blk < nblocks; ++blk) {
         u64 *B = data + blk * 64 * ct_stride;
         for (size_t lp = 0; lp < (size_t)64 * 2 * k; ++lp)
-            fwd_dispatch<RangeA>(R, lp % k, B + lp * n, B + lp * n, true);
+            fwd_dispatch(R, lp % k, B + lp * n, B + lp * n, NTT_OUT_REDUCED);
         std::vector<u64> sbuf(64 * DCT_TILE);
         for (uint32_t p = 0; p < 2; ++p)
             for (uint32_t j = 0; j < k; ++j)
                 for (uint32_t tile = 0; tile < n / DCT_TILE; ++tile) {
                     u64 *base = B + ((size_t)p * k + j) * n + (size_t)tile * DCT_TILE;
-                    u64 q = R.limbs[j].q;
+                    u64 q = R.limbs[j].q, n2q = R.limbs[j].dev.a.n2q;
                     for (int w = 0; w < 8; ++w)
                         for (int lane = 0; lane < DCT_TILE; ++lane) {
                             W2 c[DCT_NCONST];
                             for (int ci = 0; ci < DCT_NCONST; ++ci) c[ci] = ctab[j][(size_t)ci * n + tile * DCT_TILE + lane];
-                            dct_row_phase(w, lane, base, ct_stride, sbuf.data(), c, q);
+                            dct_row_phase(w, lane, base, ct_stride, sbuf.data(), c, q, n2q);
                         }
                     for (int w = 0; w < 8; ++w)
                         for (int lane = 0; lane < DCT_TILE; ++lane) {
                             W2 c[DCT_NCONST], s[8];
                             for (int ci = 0; ci < DCT_NCONST; ++ci) c[ci] = ctab[j][(size_t)ci * n + tile * DCT_TILE + lane];
                             for (int i = 0; i < 8; ++i) s[i] = stab[j][(size_t)(8 * i + w) * n + tile * DCT_TILE + lane];
-                            dct_col_phase(w, lane, base, ct_stride, sbuf.data(), c, s, q);
+                            dct_col_phase(w, lane, base, ct_stride, sbuf.data(), c, s, q, n2q);
                         }
                 }
         for (size_t lp = 0; lp < (size_t)64 * 2 * k; ++lp)
-            inv_dispatch<RangeA>(R, lp % k, B + lp * n, B + lp * n);
+            inv_dispatch(R, lp % k, B + lp * n, B + lp * n, false);
     }
     return 0;
 }

@@ -9,7 +9,6 @@ from conftest import ntt_perm
 
 u64p = C.POINTER(C.c_uint64)
 P = lambda a: a.ctypes.data_as(u64p)
-BIG61 = [0x1fffffffffe00001, 0x1fffffffffc80001]  # BEHZ m_sk, gamma: 61-bit primes
 
 
 def make_ring(E, n, qs, t=1 << 14):
@@ -19,14 +18,58 @@ def make_ring(E, n, qs, t=1 << 14):
     return r
 
 
+# a second chain next to SEAL's defaults: 50- and 41-bit primes, 1 mod 2^15
+ALT = None
+
+
+def alt_chain():
+    global ALT
+    if ALT is None:
+        import sympy
+        out, c = [], (1 << 50) // (1 << 15)
+        while len(out) < 1:
+            c -= 1
+            if sympy.isprime(c * (1 << 15) + 1):
+                out.append(c * (1 << 15) + 1)
+        c = (1 << 41) // (1 << 15)
+        while len(out) < 2:
+            c -= 1
+            if sympy.isprime(c * (1 << 15) + 1):
+                out.append(c * (1 << 15) + 1)
+        ALT = out
+    return ALT
+
+
+def test_lazy_arithmetic_ranges(emu_lib, oracle_mod):
+    """mulc in [0, 5q), reduce63 in [0, 4q), canon exact -- for arguments up to 2^63 - 1."""
+    for qs in (oracle_mod.default_coeff_modulus(4096), oracle_mod.default_coeff_modulus(2048), alt_chain()):
+        r = make_ring(emu_lib, 4096, qs)
+        rng = np.random.default_rng(7)
+        for j, q in enumerate(qs):
+            xs = [0, 1, q - 1, q, q + 1, 2 * q, 5 * q - 1, 2 ** 63 - 1, 2 ** 63 - q, (2 ** 63 // q) * q,
+                  (2 ** 63 // q) * q - 1, 2 ** 32 - 1, 2 ** 32, 2 ** 62 + 2 ** 32 - 1]
+            xs += [int(v) for v in rng.integers(0, 2 ** 63, 4000, dtype=np.uint64)]
+            ws = [0, 1, q - 1, q // 2, q // 2 + 1] + [int(v) % q for v in rng.integers(0, 2 ** 63, 40, dtype=np.uint64)]
+            for x in xs:
+                y = emu_lib.emu_reduce63(r, j, x)
+                assert y < 4 * q and y % q == x % q
+                assert emu_lib.emu_canon(r, j, x) == x % q
+            for x in xs[:200]:
+                for w in ws:
+                    y = emu_lib.emu_mulc(r, j, x, w)
+                    assert y < 5 * q and y % q == (x * w) % q, (x, w, y)
+        emu_lib.emu_ring_destroy(r)
+
+
 @pytest.mark.parametrize("n", [1024, 2048, 4096, 8192, 16384])
-@pytest.mark.parametrize("chain,rc", [("default", 0), ("default", 1), ("big61", 1)])
-def test_emulated_ntt_matches_oracle(emu_lib, oracle_mod, n, chain, rc):
-    qs = oracle_mod.default_coeff_modulus(4096) if chain == "default" else BIG61
+@pytest.mark.parametrize("chain", ["default", "alt"])
+def test_emulated_ntt_matches_oracle(emu_lib, oracle_mod, n, chain):
+    qs = oracle_mod.default_coeff_modulus(4096) if chain == "default" else alt_chain()
     o = oracle_mod.Oracle(n, qs)
     r = make_ring(emu_lib, n, qs)
-    rng = np.random.default_rng(n + rc)
+    rng = np.random.default_rng(n)
     pm = ntt_perm(n)
+    logn = n.bit_length() - 1
     for j in range(len(qs)):
         q = np.uint64(qs[j])
         assert emu_lib.emu_psi(r, j) == o.psi(j) and emu_lib.emu_delta(r, j) == o.delta_mod(j)
@@ -35,18 +78,46 @@ def test_emulated_ntt_matches_oracle(emu_lib, oracle_mod, n, chain, rc):
         ref = a.copy()
         o.ntt_forward(j, ref)
         out = np.empty(n, dtype=np.uint64)
-        assert emu_lib.emu_ntt_forward(r, j, P(a), P(out), 1, rc) == 0
+        assert emu_lib.emu_ntt_forward(r, j, P(a), P(out), 2) == 0
         assert (out[pm] == ref).all()
         lazy = np.empty(n, dtype=np.uint64)
-        emu_lib.emu_ntt_forward(r, j, P(a), P(lazy), 0, rc)
+        emu_lib.emu_ntt_forward(r, j, P(a), P(lazy), 0)
         assert ((lazy % q) == out).all()
-        bound = 64 if rc == 0 else 8
-        assert int(lazy.max()) < bound * qs[j]
-        # inverse accepts values in [0, 2q)
-        lz = out + rng.integers(0, 2, n).astype(np.uint64) * q
+        assert int(lazy.max()) < (1 + 5 * logn) * qs[j]
+        red = np.empty(n, dtype=np.uint64)
+        emu_lib.emu_ntt_forward(r, j, P(a), P(red), 1)
+        assert ((red % q) == out).all() and int(red.max()) < 4 * qs[j]
+        # inverse accepts values in [0, 5q)
+        lz = out + rng.integers(0, 5, n).astype(np.uint64) * q
         back = np.empty(n, dtype=np.uint64)
-        assert emu_lib.emu_ntt_inverse(r, j, P(lz), P(back), rc) == 0
+        assert emu_lib.emu_ntt_inverse(r, j, P(lz), P(back), 1) == 0
         assert (back == a).all()
+        # unscaled variant: n * a mod q
+        assert emu_lib.emu_ntt_inverse(r, j, P(lz), P(back), 0) == 0
+        want = np.array([(int(v) * n) % qs[j] for v in a], dtype=np.uint64)
+        assert (back == want).all()
+    emu_lib.emu_ring_destroy(r)
+
+
+def test_worst_case_inputs_stay_in_range(emu_lib, oracle_mod):
+    """all-(q-1) and all-(5q-1) inputs drive every lazy bound to its maximum."""
+    n, qs = 4096, oracle_mod.default_coeff_modulus(4096)
+    o = oracle_mod.Oracle(n, qs)
+    r = make_ring(emu_lib, n, qs)
+    pm = ntt_perm(n)
+    for j, q in enumerate(qs):
+        a = np.full(n, q - 1, dtype=np.uint64)
+        ref = a.copy()
+        o.ntt_forward(j, ref)
+        out = np.empty(n, dtype=np.uint64)
+        emu_lib.emu_ntt_forward(r, j, P(a), P(out), 2)
+        assert (out[pm] == ref).all()
+        lz = np.full(n, 5 * q - 1, dtype=np.uint64)     # == q - 1 mod q at every NTT position
+        ref2 = np.full(n, q - 1, dtype=np.uint64)[pm]   # any order: constant vector
+        o.ntt_inverse(j, ref2)
+        back = np.empty(n, dtype=np.uint64)
+        emu_lib.emu_ntt_inverse(r, j, P(lz), P(back), 1)
+        assert (back == ref2).all()
     emu_lib.emu_ring_destroy(r)
 
 
@@ -77,6 +148,7 @@ def test_ring_rejects_bad_parameters(emu_lib):
         (4096, [0x7fffffff380003]),            # not 1 mod 2n / not prime
         (4096, [0x7fffffff380001] * 2),        # duplicate prime
         (4096, [12289]),                       # <= t
+        (4096, [0x1fffffffffe00001]),          # 61-bit prime: valid SEAL modulus, unsupported by this build
     ]
     for n, qs in bad:
         assert not emu_lib.emu_ring_create(n, len(qs), (C.c_uint64 * len(qs))(*qs), 1 << 14, err, 256)
