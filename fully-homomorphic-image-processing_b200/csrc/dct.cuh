@@ -68,30 +68,39 @@ constexpr int DCT_ROW_INB = 4;
 
 // Row phase for (row r, lane): block rows are ciphertexts 8r..8r+7 (fhe_image.h:192-195).
 // in: pointer to (ct 0, this poly, this limb, first position of the tile); ct_stride in u64.
+FHE_HD void dct_row_load(int r, int lane, const u64 *__restrict__ in, size_t ct_stride, u64 *d)
+{
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[i] = in[(size_t)(8 * r + i) * ct_stride + lane];
+}
+FHE_HD void dct_row_compute(int r, int lane, u64 *d, u64 *sbuf, const W2 *c, u64 q, u64 n2q)
+{
+    dct8_pass<DCT_ROW_INB>(d, c, q, n2q);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sbuf[(8 * r + i) * DCT_TILE + lane] = d[i];
+}
 FHE_HD void dct_row_phase(int r, int lane, const u64 *__restrict__ in, size_t ct_stride, u64 *sbuf,
                           const W2 *c, u64 q, u64 n2q)
 {
     u64 d[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) d[i] = in[(size_t)(8 * r + i) * ct_stride + lane];
-    dct8_pass<DCT_ROW_INB>(d, c, q, n2q);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) sbuf[(8 * r + i) * DCT_TILE + lane] = d[i];
+    dct_row_load(r, lane, in, ct_stride, d);
+    dct_row_compute(r, lane, d, sbuf, c, q, n2q);
 }
 
 // Column phase for (column col, lane): 1-D pass down the column, then one multiplication per
 // output by the merged scale constant  s[i] = NTT(0.125) * NTT(1/quant[8i+col])  (or NTT(0.125)
 // alone when no quantisation table is attached), times n^-1 so the inverse NTT that follows skips
 // its own scaling.  Output < 5q (inverse-NTT input range).
+// s: scale constants of outputs (row i, this column), s[i * s_stride]
 FHE_HD void dct_col_phase(int col, int lane, u64 *__restrict__ out, size_t ct_stride, const u64 *sbuf,
-                          const W2 *c, const W2 *s, u64 q, u64 n2q)
+                          const W2 *c, const W2 *__restrict__ s, size_t s_stride, u64 q, u64 n2q)
 {
     u64 d[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = sbuf[(8 * i + col) * DCT_TILE + lane];
     dct8_pass<8 * DCT_ROW_INB>(d, c, q, n2q);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) out[(size_t)(8 * i + col) * ct_stride + lane] = mulc(d[i], s[i], n2q);
+    for (int i = 0; i < 8; ++i) out[(size_t)(8 * i + col) * ct_stride + lane] = mulc(d[i], s[i * s_stride], n2q);
 }
 
 }  // namespace fhe

@@ -115,7 +115,9 @@ k_mulplain(const u64 *in, u64 *out, const W2 *__restrict__ table, RingDev R)
 // =============================================================================================
 // CTA = 8 warps on one (limb, 32-position tile); loops over `upc` consecutive units
 // (unit = one poly of one block: 64 limb-polys, one per ciphertext of the block) so the
-// 12 + 8 Shoup constants a thread needs stay in registers across units.
+// 12 + 8 constants a thread needs stay in registers across units.  (Re-reading the 8 scale
+// constants per unit from L1 and prefetching the next unit's inputs instead measured 9 % slower
+// on B200, and a 3-CTA/SM register cap spills: profiles/r01_notes.md.)
 __global__ void __launch_bounds__(256, 2)
 k_dct_pointwise(u64 *data, const W2 *__restrict__ ctab, const W2 *__restrict__ stab, RingDev R,
                 unsigned long long nunits, int upc)
@@ -142,7 +144,7 @@ k_dct_pointwise(u64 *data, const W2 *__restrict__ ctab, const W2 *__restrict__ s
         u64 *sb = sbuf[it & 1];
         dct_row_phase(w, lane, base, ct_stride, sb, c, q, n2q);
         __syncthreads();
-        dct_col_phase(w, lane, base, ct_stride, sb, c, s, q, n2q);
+        dct_col_phase(w, lane, base, ct_stride, sb, c, s, 1, q, n2q);
     }
 }
 

@@ -170,7 +170,7 @@ int emu_dct_quant(void *r, uint64_t *data_, uint64_t nblocks, const uint64_t *pl
                             W2 c[DCT_NCONST], s[8];
                             for (int ci = 0; ci < DCT_NCONST; ++ci) c[ci] = ctab[j][(size_t)ci * n + tile * DCT_TILE + lane];
                             for (int i = 0; i < 8; ++i) s[i] = stab[j][(size_t)(8 * i + w) * n + tile * DCT_TILE + lane];
-                            dct_col_phase(w, lane, base, ct_stride, sbuf.data(), c, s, q, n2q);
+                            dct_col_phase(w, lane, base, ct_stride, sbuf.data(), c, s, 1, q, n2q);
                         }
                 }
         for (size_t lp = 0; lp < (size_t)64 * 2 * k; ++lp)
