@@ -85,15 +85,21 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_sample(threads, blocks):
-    """Oracle (CPU restatement of the reference's op-by-op graph) on a bounded sample."""
+def cpu_sample(threads, blocks, min_seconds=0.0):
+    """Oracle (CPU restatement of the reference's op-by-op graph) on a bounded sample: `blocks`
+    blocks per pass, repeated on fresh inputs until `min_seconds` of CPU work were timed."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
     pkg = importlib.import_module("fully-homomorphic-image-processing_b200")
     o = oracle_py.Oracle(N_RING, None, T_PLAIN)
-    data = o.fill_uniform(0, 64 * blocks)
-    secs = o.bench_dct_quant(data, blocks, pkg.YQT, threads)
-    return blocks / secs, secs
+    secs, done = 0.0, 0
+    while True:
+        data = o.fill_uniform(64 * done, 64 * blocks)
+        secs += o.bench_dct_quant(data, blocks, pkg.YQT, threads)
+        done += blocks
+        if secs >= min_seconds:
+            break
+    return done / secs, secs, done
 
 
 def run_reference(args, rank, world):
@@ -103,12 +109,12 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    blocks = max(threads, min(2 * threads, 128))
+    blocks = 8 * threads                      # ~1 s of CPU work per step on the GPU box's host cores
     for _ in range(args.warmup):
         cpu_sample(threads, max(1, threads // 2))
     t = 0.0
     for _ in range(args.steps):
-        _, s = cpu_sample(threads, blocks)
+        _, s, _ = cpu_sample(threads, blocks)
         t += s
     value = blocks * args.steps / t
     sample = f"{blocks} blocks/step (64 size-2 cts each, n=4096 k=2), {threads} threads, op-by-op graph"
@@ -264,11 +270,10 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        blocks = max(threads, min(4 * threads, 128))
-        v, secs = cpu_sample(threads, blocks)
-        v1, _ = cpu_sample(1, 4)
+        v, secs, done = cpu_sample(threads, 8 * threads, min_seconds=12.0)
+        v1, _, _ = cpu_sample(1, 4)
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{blocks} blocks of the same workload in {secs:.2f} s on {threads} threads "
+               "sample": f"{done} blocks of the same workload in {secs:.1f} s on {threads} threads "
                          f"(oracle, op-by-op reference graph); single thread: {v1:.2f} blocks/s",
                "single_thread_value": v1}
 

@@ -581,6 +581,14 @@ int fhe_download(fhe_ctx *c, void *dst, const void *src, size_t bytes)
     return FHE_OK;
 }
 
+int fhe_device_copy(fhe_ctx *c, void *dst, const void *src, size_t bytes)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!dst || !src) return fail(FHE_ERR_INVALID_ARGUMENT, "null buffer");
+    CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return FHE_OK;
+}
+
 // FractionalEncoder(t, poly_modulus, int_coeffs, frac_coeffs, 2).encode:
 // integer part in binary from x^0 up; i-th fractional binary digit d_i (weight 2^-(i+1)) stored
 // as -d_i at x^(n-1-i) because x^n = -1; negative values negate every digit; all mod t.

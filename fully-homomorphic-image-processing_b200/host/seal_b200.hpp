@@ -1,0 +1,298 @@
+// seal_b200.hpp -- seal::-shaped C++ value types over the C-ABI of libfhe_b200.so.
+//
+// The reference's image-op headers (homo/fhe_image.h, fhe_resize.h, fhe_decode.h) are written
+// against seal::Evaluator / Ciphertext / Plaintext / FractionalEncoder.  This
+// header gives the same names, argument meaning and error behaviour for the subset those
+// headers use on the server side, with the ciphertext data resident in B200 HBM:
+//
+//   seal::EncryptionParameters / SEALContext   server_jpeg.cpp:74-80   -> Context
+//   seal::FractionalEncoder(t, poly, 100, 100, 2)   server_jpeg.cpp:100 -> FractionalEncoder
+//   seal::Ciphertext (value type, copied freely)    fhe_image.h:207     -> Ciphertext
+//   seal::Evaluator::{add, sub, negate, multiply_plain, add_plain, sub_plain}  (in place on the
+//   first argument, second const; std::invalid_argument on mismatch or zero plaintext)
+//                                                   fhe_image.h:207-325 -> Evaluator
+//   seal::Encryptor (only passed through by fhe_image.h)                -> Encryptor (opaque)
+//
+// Everything computes on the device through include/fhe_b200.h; there is no CPU path.
+// Host language: C++17, no dependency besides the C-ABI header.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/fhe_b200.h"
+
+namespace seal_b200 {
+
+inline void check(int rc)
+{
+    if (rc == FHE_OK) return;
+    const std::string msg = fhe_last_error();
+    if (rc == FHE_ERR_INVALID_ARGUMENT || rc == FHE_ERR_ZERO_PLAIN) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+}
+
+// EncryptionParameters + SEALContext: ring degree n ("--cmod" in the reference, a naming quirk,
+// server_jpeg.cpp:76), coeff_modulus_128(n) unless a chain is given, plain_modulus t.
+class Context {
+public:
+    explicit Context(uint32_t n, uint64_t plain_modulus = 1 << 14, std::vector<uint64_t> coeff_modulus = {},
+                     int device = 0)
+        : n_(n), t_(plain_modulus), q_(std::move(coeff_modulus))
+    {
+        if (q_.empty()) {
+            uint64_t buf[16];
+            uint32_t k = 0;
+            check(fhe_default_coeff_modulus(n, buf, &k));
+            q_.assign(buf, buf + k);
+        }
+        check(fhe_ctx_create(n, (uint32_t)q_.size(), q_.data(), t_, device, nullptr, &h_));
+    }
+    ~Context() { fhe_ctx_destroy(h_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+
+    fhe_ctx *handle() const { return h_; }
+    uint32_t poly_degree() const { return n_; }
+    uint32_t coeff_mod_count() const { return (uint32_t)q_.size(); }
+    const std::vector<uint64_t> &coeff_modulus() const { return q_; }
+    uint64_t plain_modulus() const { return t_; }
+    size_t ct_words(uint32_t size = 2) const { return (size_t)size * q_.size() * n_; }
+    void sync() const { check(fhe_ctx_sync(h_)); }
+
+private:
+    uint32_t n_;
+    uint64_t t_;
+    std::vector<uint64_t> q_;
+    fhe_ctx *h_ = nullptr;
+};
+
+// seal::Plaintext: n coefficients in [0, t).
+class Plaintext {
+public:
+    Plaintext() = default;
+    explicit Plaintext(std::vector<uint64_t> c) : coeffs_(std::move(c)) {}
+    const std::vector<uint64_t> &coeffs() const { return coeffs_; }
+    bool is_zero() const
+    {
+        for (uint64_t v : coeffs_)
+            if (v) return false;
+        return true;
+    }
+
+private:
+    std::vector<uint64_t> coeffs_;
+};
+
+// seal::FractionalEncoder (binary base; the reference's --base override is dead code).
+class FractionalEncoder {
+public:
+    FractionalEncoder(const Context &ctx, uint32_t integer_coeff_count = 100, uint32_t fraction_coeff_count = 100,
+                      uint32_t base = 2)
+        : n_(ctx.poly_degree()), t_(ctx.plain_modulus()), ic_(integer_coeff_count), fc_(fraction_coeff_count),
+          base_(base)
+    {
+    }
+    Plaintext encode(double value) const
+    {
+        std::vector<uint64_t> c(n_);
+        check(fhe_frac_encode(n_, t_, value, ic_, fc_, base_, c.data()));
+        return Plaintext(std::move(c));
+    }
+
+private:
+    uint32_t n_;
+    uint64_t t_;
+    uint32_t ic_, fc_, base_;
+};
+
+// Device memory shared by the ciphertexts carved out of it (a block of 64 loaded together stays
+// contiguous, so the fused kernels can run on it in place).
+class Arena {
+public:
+    Arena(const Context &ctx, size_t words) : ctx_(&ctx), words_(words)
+    {
+        void *p = nullptr;
+        check(fhe_device_alloc(ctx.handle(), words * sizeof(uint64_t), &p));
+        d_ = (uint64_t *)p;
+    }
+    ~Arena() { fhe_device_free(ctx_->handle(), d_); }
+    Arena(const Arena &) = delete;
+    Arena &operator=(const Arena &) = delete;
+    uint64_t *data() const { return d_; }
+    size_t words() const { return words_; }
+
+private:
+    const Context *ctx_;
+    uint64_t *d_ = nullptr;
+    size_t words_;
+};
+
+// seal::Ciphertext: a value type.  Copy construction / assignment duplicate the device data
+// (the reference copies ciphertexts ~1500 times per block, fhe_image.h:207-284).
+class Ciphertext {
+public:
+    Ciphertext() = default;
+    Ciphertext(const Context &ctx, uint32_t size = 2) : ctx_(&ctx), size_(size)
+    {
+        arena_ = std::make_shared<Arena>(ctx, ctx.ct_words(size));
+        d_ = arena_->data();
+    }
+    // a view of `size` polys at `d` inside a shared arena (see load_block)
+    Ciphertext(const Context &ctx, std::shared_ptr<Arena> arena, uint64_t *d, uint32_t size)
+        : ctx_(&ctx), arena_(std::move(arena)), d_(d), size_(size), view_(true)
+    {
+    }
+    Ciphertext(const Ciphertext &o) : ctx_(o.ctx_), size_(o.size_)
+    {
+        if (!o.d_) return;
+        arena_ = std::make_shared<Arena>(*ctx_, ctx_->ct_words(size_));
+        d_ = arena_->data();
+        check(fhe_device_copy(ctx_->handle(), d_, o.d_, ctx_->ct_words(size_) * sizeof(uint64_t)));
+    }
+    Ciphertext(Ciphertext &&o) noexcept : ctx_(o.ctx_), arena_(std::move(o.arena_)), d_(o.d_), size_(o.size_), view_(o.view_)
+    {
+        o.d_ = nullptr;
+    }
+    // Assigning into a view (an element of a block loaded by load_block) overwrites the view's
+    // storage, so `data[i] = tmp` keeps the block contiguous; otherwise this is a deep copy.
+    Ciphertext &operator=(const Ciphertext &o)
+    {
+        if (this == &o) return *this;
+        if (!o.d_) throw std::invalid_argument("assignment from an empty ciphertext");
+        const bool reuse = d_ && ctx_ == o.ctx_ && size_ == o.size_;
+        if (!reuse) {
+            if (view_) throw std::invalid_argument("cannot resize a ciphertext that lives inside a block");
+            ctx_ = o.ctx_;
+            size_ = o.size_;
+            arena_ = std::make_shared<Arena>(*ctx_, ctx_->ct_words(size_));
+            d_ = arena_->data();
+        }
+        check(fhe_device_copy(ctx_->handle(), d_, o.d_, ctx_->ct_words(size_) * sizeof(uint64_t)));
+        return *this;
+    }
+    Ciphertext &operator=(Ciphertext &&o)
+    {
+        if (this == &o) return *this;
+        if (view_ || o.view_) return *this = static_cast<const Ciphertext &>(o);
+        ctx_ = o.ctx_; arena_ = std::move(o.arena_); d_ = o.d_; size_ = o.size_;
+        o.d_ = nullptr;
+        return *this;
+    }
+
+    uint32_t size() const { return size_; }
+    uint64_t *device_data() const { return d_; }
+    const Context *context() const { return ctx_; }
+    bool valid() const { return d_ != nullptr; }
+
+    // host <-> device, layout [poly][limb][n] (drop SEAL 2.3's padding coefficient when importing)
+    void upload(const uint64_t *host) { check(fhe_upload(ctx_->handle(), d_, host, ctx_->ct_words(size_) * 8)); }
+    void download(uint64_t *host) const { check(fhe_download(ctx_->handle(), host, d_, ctx_->ct_words(size_) * 8)); }
+
+private:
+    const Context *ctx_ = nullptr;
+    std::shared_ptr<Arena> arena_;
+    uint64_t *d_ = nullptr;
+    uint32_t size_ = 0;
+    bool view_ = false;
+};
+
+// `count` size-2 ciphertexts in one contiguous device allocation (what server_jpeg.cpp holds after
+// loading the 64 ciphertexts of a block, :115-124).  host may be null (uninitialised storage).
+inline std::vector<Ciphertext> load_block(const Context &ctx, const uint64_t *host, size_t count, uint32_t size = 2)
+{
+    const size_t w = ctx.ct_words(size);
+    auto arena = std::make_shared<Arena>(ctx, w * count);
+    if (host) check(fhe_upload(ctx.handle(), arena->data(), host, w * count * sizeof(uint64_t)));
+    std::vector<Ciphertext> v;
+    v.reserve(count);
+    for (size_t i = 0; i < count; ++i) v.emplace_back(ctx, arena, arena->data() + i * w, size);
+    return v;
+}
+// true when the ciphertexts are consecutive in one allocation, in order
+inline bool is_contiguous(const std::vector<Ciphertext> &v)
+{
+    if (v.empty() || !v[0].valid()) return false;
+    const size_t w = v[0].context()->ct_words(v[0].size());
+    for (size_t i = 0; i < v.size(); ++i)
+        if (!v[i].valid() || v[i].size() != v[0].size() || v[i].device_data() != v[0].device_data() + i * w) return false;
+    return true;
+}
+
+class Encryptor {  // passed through by fhe_image.h, never used on the JPEG path
+};
+
+// seal::Evaluator.  Plaintext operands are transformed once and cached by content (the reference
+// re-encodes and re-transforms the same 13 + 64 + 9 constants on every call).
+class Evaluator {
+public:
+    explicit Evaluator(const Context &ctx) : ctx_(&ctx) {}
+    ~Evaluator()
+    {
+        for (auto &kv : cache_) fhe_ptab_destroy(kv.second);
+    }
+    Evaluator(const Evaluator &) = delete;
+    Evaluator &operator=(const Evaluator &) = delete;
+
+    void add(Ciphertext &a, const Ciphertext &b) { binary(a, b, fhe_add); }
+    void sub(Ciphertext &a, const Ciphertext &b) { binary(a, b, fhe_sub); }
+    void negate(Ciphertext &a)
+    {
+        require(a);
+        check(fhe_negate(ctx_->handle(), a.device_data(), 1, a.size()));
+    }
+    void multiply_plain(Ciphertext &a, const Plaintext &p)
+    {
+        require(a);
+        if (p.is_zero()) throw std::invalid_argument("plain cannot be zero");
+        check(fhe_multiply_plain(ctx_->handle(), a.device_data(), 1, a.size(), table(p), 0));
+    }
+    void add_plain(Ciphertext &a, const Plaintext &p)
+    {
+        require(a);
+        check(fhe_add_plain(ctx_->handle(), a.device_data(), 1, a.size(), table(p), 0));
+    }
+    void sub_plain(Ciphertext &a, const Plaintext &p)
+    {
+        require(a);
+        check(fhe_sub_plain(ctx_->handle(), a.device_data(), 1, a.size(), table(p), 0));
+    }
+    const Context &context() const { return *ctx_; }
+    // per-evaluator cache slot for the fused-graph plans of fhe_image_b200.hpp
+    std::shared_ptr<void> &plan_slot(const std::string &key) { return plans_[key]; }
+
+private:
+    void require(const Ciphertext &a) const
+    {
+        if (!a.valid() || a.context() != ctx_) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    }
+    template <class F>
+    void binary(Ciphertext &a, const Ciphertext &b, F fn)
+    {
+        require(a);
+        require(b);
+        // SEAL allows unequal sizes (result = max); the JPEG path only ever meets size 2.
+        if (a.size() != b.size()) throw std::invalid_argument("ciphertext sizes differ (not needed by fhe_image.h)");
+        check(fn(ctx_->handle(), a.device_data(), b.device_data(), 1, a.size()));
+    }
+    fhe_ptab *table(const Plaintext &p)
+    {
+        if (p.coeffs().size() != ctx_->poly_degree()) throw std::invalid_argument("plain is not valid for encryption parameters");
+        std::string key((const char *)p.coeffs().data(), p.coeffs().size() * sizeof(uint64_t));
+        auto it = cache_.find(key);
+        if (it != cache_.end()) return it->second;
+        fhe_ptab *t = nullptr;
+        check(fhe_ptab_create(ctx_->handle(), p.coeffs().data(), 1, &t));
+        cache_.emplace(std::move(key), t);
+        return t;
+    }
+    const Context *ctx_;
+    std::unordered_map<std::string, fhe_ptab *> cache_;
+    std::unordered_map<std::string, std::shared_ptr<void>> plans_;
+};
+
+}  // namespace seal_b200

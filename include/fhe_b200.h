@@ -69,6 +69,9 @@ int fhe_host_alloc(size_t bytes, void **hptr); /* pinned */
 int fhe_host_free(void *hptr);
 int fhe_upload(fhe_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);   /* synchronous */
 int fhe_download(fhe_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* synchronous */
+/* device -> device on the context's stream: seal::Ciphertext copy construction / assignment
+ * (`Ciphertext boaz1(data[0])`, fhe_image.h:207). */
+int fhe_device_copy(fhe_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
 
 /* ---- encoder (host logic) -----------------------------------------------------------------
  * seal::FractionalEncoder(plain_modulus, poly_modulus, int_coeffs, frac_coeffs, base).encode,
