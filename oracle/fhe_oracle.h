@@ -103,6 +103,48 @@ uint64_t orc_checksum(const uint64_t *v, uint64_t count);
 double orc_bench_dct_quant(const orc_ctx *c, uint64_t *data, uint64_t nblocks, const double *quant,
                            uint32_t int_coeffs, uint32_t frac_coeffs, int nthreads);
 
+/* ==== part 2 (fhe_oracle_behz.c): ciphertext x ciphertext ops and the graphs built on them ====
+ * BEHZ full-RNS multiply/square and relinearize restated from SURVEY.md Appendix A.6-A.7
+ * ([SEAL-recall]; PARITY UNPINNED), anchored on fhe_resize.h:174-179,197-198 and
+ * fhe_decode.h:67-97,147-177,235,239. */
+typedef struct orc_behz orc_behz;
+orc_behz *orc_behz_create(const orc_ctx *c);
+void orc_behz_destroy(orc_behz *b);
+uint32_t orc_behz_aux_count(const orc_behz *b);           /* |B| */
+uint64_t orc_behz_bsk(const orc_behz *b, uint32_t j);      /* B_sk primes, m_sk last */
+/* steps 1-2 (fastbconv_mtilde + mont_rq): x [k][n] in base q -> out [|B|+1][n] in base Bsk */
+void orc_behz_extend(const orc_behz *b, const uint64_t *x, uint64_t *out);
+/* steps 6-8 (times t, fast_floor, fastbconv_sk): xq [k][n], xb [|B|+1][n] -> out [k][n] */
+void orc_behz_scale_round(const orc_behz *b, const uint64_t *xq, const uint64_t *xb, uint64_t *out);
+/* Evaluator::multiply / square; dest has s1 + s2 - 1 (2 s - 1) polys, must not alias inputs. */
+void orc_multiply(const orc_behz *b, const uint64_t *a1, uint32_t s1, const uint64_t *a2, uint32_t s2,
+                  uint64_t *dest);
+void orc_square(const orc_behz *b, const uint64_t *a, uint32_t s, uint64_t *dest);
+
+/* harness (client side in the reference): keys, encryption, decryption phase, evaluation keys.
+ * sk [k][n]; pk [2][k][n]; all polynomials in coefficient form. */
+void orc_keygen(const orc_behz *b, uint64_t seed, uint64_t *sk, uint64_t *pk);
+void orc_encrypt(const orc_behz *b, const uint64_t *pk, const uint64_t *plain, uint32_t plain_len,
+                 uint64_t seed, uint64_t *ct);
+void orc_phase(const orc_behz *b, const uint64_t *sk, const uint64_t *ct, uint32_t size, uint64_t *out);
+uint32_t orc_evk_digits(const orc_behz *b, uint32_t dbc);
+/* evk layout [count][k][digits][2][k][n], coefficient form */
+void orc_evk_gen(const orc_behz *b, const uint64_t *sk, uint32_t dbc, uint32_t count, uint64_t seed,
+                 uint64_t *evk);
+void orc_relinearize(const orc_behz *b, const uint64_t *ct, uint32_t size, const uint64_t *evk,
+                     uint32_t dbc, uint32_t evk_count, uint64_t *dest);
+
+/* reference graphs; each returns the size of the result ciphertext(s) */
+uint32_t orc_cubic(const orc_behz *b, const uint64_t *const in[4], const uint32_t sz[4],
+                   const uint64_t *t, uint32_t st, uint32_t ic, uint32_t fc, uint64_t *out);
+uint32_t orc_linear(const orc_behz *b, const uint64_t *A, uint32_t sA, const uint64_t *B, uint32_t sB,
+                    const uint64_t *t, uint32_t st, uint32_t ic, uint32_t fc, uint64_t *out);
+uint32_t orc_homomorphic_sincos(const orc_behz *b, const uint64_t *x, uint32_t sx, const uint64_t *zero,
+                                int is_cos, uint32_t ic, uint32_t fc, uint64_t *out);
+uint32_t orc_approximated_step(const orc_behz *b, const uint64_t *amplitude, const uint64_t *index,
+                               const uint64_t *count, int order, int degree, double delta, int npos,
+                               const uint64_t *zeros, uint32_t ic, uint32_t fc, uint64_t *run_out);
+
 #ifdef __cplusplus
 }
 #endif

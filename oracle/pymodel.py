@@ -191,3 +191,99 @@ class Model:
                 worst = max(worst, err)
             out.append(m % t)
         return (out, worst) if return_noise else out
+
+
+# SEAL 2.3.1 internal_mods ([SEAL-recall]): largest primes below 2^61 that are
+# 1 mod 2^18, descending: m_sk, gamma, then the auxiliary base.
+M_SK = 0x1FFFFFFFFFE00001
+AUX_SMALL_MODS = [0x1FFFFFFFFFB40001, 0x1FFFFFFFFF500001, 0x1FFFFFFFFF380001, 0x1FFFFFFFFF000001,
+                  0x1FFFFFFFFEF00001, 0x1FFFFFFFFEE80001, 0x1FFFFFFFFEB40001, 0x1FFFFFFFFE780001,
+                  0x1FFFFFFFFE600001, 0x1FFFFFFFFE4C0001]
+M_TILDE = 1 << 32
+
+
+class Behz:
+    """BEHZ full-RNS multiply on Python ints: every fast base conversion
+    is the exact big-integer sum  S = sum_i y_i (q/q_i)  reduced afterwards, the Montgomery step is
+    an exact integer division -- no Barrett, no NTT, no 128-bit accumulators, so nothing is shared
+    with oracle/fhe_oracle_behz.c or the CUDA kernels beyond the specification itself."""
+
+    def __init__(self, m: Model):
+        self.m = m
+        k = len(m.qs)
+        bits = sum(q.bit_length() for q in m.qs)
+        kb = k + (1 if 32 + m.t.bit_length() + bits >= 61 * k + 61 else 0)
+        self.B = AUX_SMALL_MODS[:kb]
+        self.bsk = self.B + [M_SK]
+        self.Bprod = prod(self.B)
+
+    def _conv_sum(self, res, mods, total):
+        """sum_i [res_i (M/m_i)^-1]_{m_i} (M/m_i): the uncorrected fast base conversion."""
+        s = 0
+        for r, mi in zip(res, mods):
+            hat = total // mi
+            s += (r * pow(hat % mi, -1, mi) % mi) * hat
+        return s
+
+    def extend(self, poly):
+        """poly: n ints mod q -> [len(bsk)][n] residues (fastbconv_mtilde + mont_rq)."""
+        m, q = self.m, self.m.q
+        out = [[0] * m.n for _ in self.bsk]
+        for c, x in enumerate(poly):
+            s = self._conv_sum([(x % qi) * M_TILDE % qi for qi in m.qs], m.qs, q)
+            r = (-s * pow(q, -1, M_TILDE)) % M_TILDE
+            if r >= M_TILDE // 2:
+                r -= M_TILDE
+            v, rem = divmod(s + q * r, M_TILDE)
+            assert rem == 0
+            for j, p in enumerate(self.bsk):
+                out[j][c] = v % p
+        return out
+
+    def scale_round(self, xq, xb):
+        """xq: [k][n] residues, xb: [len(bsk)][n] -> n ints mod q (times t, fast_floor, fastbconv_sk)."""
+        m, q, t = self.m, self.m.q, self.m.t
+        out = []
+        for c in range(m.n):
+            s = self._conv_sum([t * xq[i][c] % qi for i, qi in enumerate(m.qs)], m.qs, q)
+            f = [(t * xb[j][c] - s) * pow(q, -1, p) % p for j, p in enumerate(self.bsk)]
+            s2 = self._conv_sum(f[:-1], self.B, self.Bprod)
+            alpha = (s2 - f[-1]) * pow(self.Bprod, -1, M_SK) % M_SK
+            if alpha > M_SK // 2:
+                alpha -= M_SK
+            out.append((s2 - alpha * self.Bprod) % q)   # CRT of the per-limb results
+        return out
+
+    def multiply(self, a, b):
+        """a, b: lists of polys (ints mod q) -> list of len(a)+len(b)-1 polys."""
+        m = self.m
+        ea, eb = [self.extend(p) for p in a], [self.extend(p) for p in b]
+        out = []
+        for l in range(len(a) + len(b) - 1):
+            accq = [[0] * m.n for _ in m.qs]
+            accb = [[0] * m.n for _ in self.bsk]
+            for x in range(len(a)):
+                y = l - x
+                if y < 0 or y >= len(b):
+                    continue
+                for i, qi in enumerate(m.qs):
+                    pr = m.poly_mul([v % qi for v in a[x]], [v % qi for v in b[y]], qi)
+                    accq[i] = [(u + v) % qi for u, v in zip(accq[i], pr)]
+                for j, p in enumerate(self.bsk):
+                    pr = m.poly_mul(ea[x][j], eb[y][j], p)
+                    accb[j] = [(u + v) % p for u, v in zip(accb[j], pr)]
+            out.append(self.scale_round(accq, accb))
+        return out
+
+    def relinearize(self, ct, evk, dbc):
+        """evk[r][i][l] = (k0, k1) polys mod q; SURVEY A.7."""
+        m = self.m
+        ct = [list(p) for p in ct]
+        while len(ct) > 2:
+            last, r = ct.pop(), len(ct) - 2
+            for i, qi in enumerate(m.qs):
+                for l, (k0, k1) in enumerate(evk[r][i]):
+                    d = [((c % qi) >> (l * dbc)) & ((1 << dbc) - 1) for c in last]
+                    ct[0] = m.poly_add(ct[0], m.poly_mul(d, k0))
+                    ct[1] = m.poly_add(ct[1], m.poly_mul(d, k1))
+        return ct
