@@ -45,7 +45,8 @@ class FheError(RuntimeError):
 def build(force: bool = False) -> str:
     """Compile csrc/ for sm_100a into the in-tree libfhe_b200.so (nvcc cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc", "fhe_b200.cu")
-    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in ("ntt.cuh", "dct.cuh", "modarith.cuh", "ring_host.hpp")]
+    deps = [src] + [os.path.join(_HERE, "csrc", f) for f in (
+        "ntt.cuh", "dct.cuh", "modarith.cuh", "ring_host.hpp", "ntt_wide.cuh", "behz.cuh", "behz_host.hpp", "behz_api.inc")]
     deps.append(os.path.join(ROOT, "include", "fhe_b200.h"))
     stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if force or stale:
@@ -101,6 +102,12 @@ def lib():
         "fhe_set_dct_chunk_blocks": (i32, [vp, u32]),
         "fhe_set_stage_timing": (i32, [vp, i32]),
         "fhe_get_stage_times": (i32, [vp, C.POINTER(C.c_float)]),
+        "fhe_multiply": (i32, [vp, vp, u32, vp, u32, vp, u64]),
+        "fhe_square": (i32, [vp, vp, u32, vp, u64]),
+        "fhe_evk_digits": (u32, [vp, u32]),
+        "fhe_evk_create": (i32, [vp, u64p, u32, u32, C.POINTER(vp)]),
+        "fhe_evk_destroy": (None, [vp]),
+        "fhe_relinearize": (i32, [vp, vp, u32, vp, vp, u64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -117,6 +124,7 @@ EXPORTED_SYMBOLS = (
     "fhe_ntt_forward", "fhe_ntt_inverse", "fhe_dct_plan_create", "fhe_dct_plan_destroy",
     "fhe_dct8x8_quantize", "fhe_dct8x8_quantize_host", "fhe_fill_uniform", "fhe_checksum",
     "fhe_launch_count", "fhe_set_dct_chunk_blocks", "fhe_set_stage_timing", "fhe_get_stage_times",
+    "fhe_multiply", "fhe_square", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
 )
 
 
@@ -213,6 +221,18 @@ class Context:
     def sub_plain(self, a, n_ct, tab: "PlainTable", index=0, size=2):
         _check(lib().fhe_sub_plain(self.h, C.c_void_p(a), n_ct, size, tab.h, index))
 
+    def multiply(self, a, size_a, b, size_b, dest, n_ct=1):
+        """Evaluator::multiply: dest [n_ct][size_a + size_b - 1][k][n] (device pointers)."""
+        _check(lib().fhe_multiply(self.h, C.c_void_p(a), size_a, C.c_void_p(b), size_b, C.c_void_p(dest), n_ct))
+
+    def square(self, a, size_a, dest, n_ct=1):
+        _check(lib().fhe_square(self.h, C.c_void_p(a), size_a, C.c_void_p(dest), n_ct))
+
+    def evk_digits(self, dbc: int) -> int: return int(lib().fhe_evk_digits(self.h, dbc))
+
+    def relinearize(self, a, size, evk: "EvaluationKeys", dest, n_ct=1):
+        _check(lib().fhe_relinearize(self.h, C.c_void_p(a), size, evk.h, C.c_void_p(dest), n_ct))
+
     def ntt_forward(self, a, n_limbpolys): _check(lib().fhe_ntt_forward(self.h, C.c_void_p(a), n_limbpolys))
     def ntt_inverse(self, a, n_limbpolys): _check(lib().fhe_ntt_inverse(self.h, C.c_void_p(a), n_limbpolys))
 
@@ -253,6 +273,30 @@ class PlainTable:
     def close(self):
         if getattr(self, "h", None) and self.ctx.h:
             lib().fhe_ptab_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class EvaluationKeys:
+    """seal::EvaluationKeys of generate_evaluation_keys(dbc, count) (tests/parameters.cpp:89-90),
+    given in coefficient form [count][k][digits][2][k][n] and kept NTT-transformed on the device."""
+
+    def __init__(self, ctx: Context, evk, dbc: int, count: int):
+        import numpy as np
+        arr = np.ascontiguousarray(evk, dtype=np.uint64).reshape(-1)
+        assert arr.size == count * ctx.k * ctx.evk_digits(dbc) * 2 * ctx.k * ctx.n
+        h = C.c_void_p()
+        _check(lib().fhe_evk_create(ctx.h, _np_ptr(arr), dbc, count, C.byref(h)))
+        self.h, self.ctx, self.dbc, self.count = h, ctx, dbc, count
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().fhe_evk_destroy(self.h)
         self.h = None
 
     def __del__(self):

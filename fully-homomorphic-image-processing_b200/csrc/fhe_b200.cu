@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/fhe_b200.h"
+#include "behz_host.hpp"
 #include "dct.cuh"
 #include "ntt.cuh"
 #include "ring_host.hpp"
@@ -286,7 +287,10 @@ struct fhe_ctx {
     // optional per-kernel timing of the DCT path
     bool stage_timing = false;
     std::vector<cudaEvent_t> stage_ev;  // 4 per chunk of the last call
+    // Evaluator::multiply / square / relinearize state, built on first use (behz_api.inc)
+    struct BehzState *behz = nullptr;
 };
+static void behz_state_destroy(struct BehzState *s);
 struct fhe_ptab {
     fhe_ctx *ctx = nullptr;
     uint32_t count = 0;
@@ -495,6 +499,7 @@ void fhe_ctx_destroy(fhe_ctx *c)
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
     clear_stage_events(c);
+    behz_state_destroy(c->behz);
     cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_scratch);
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
@@ -917,3 +922,5 @@ int fhe_checksum(fhe_ctx *c, const uint64_t *d, uint64_t count, uint64_t *out)
 }
 
 }  // extern "C"
+
+#include "behz_api.inc"

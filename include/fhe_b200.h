@@ -130,6 +130,35 @@ int fhe_dct8x8_quantize(fhe_ctx *ctx, const fhe_dct_plan *plan, const uint64_t *
 int fhe_dct8x8_quantize_host(fhe_ctx *ctx, const fhe_dct_plan *plan, const uint64_t *h_in,
                              uint64_t *h_out, uint64_t nblocks);
 
+/* ---- Evaluator: ciphertext x ciphertext ----------------------------------------------------
+ * Evaluator::multiply(a, b) (fhe_resize.h:175-179,197-198; fhe_decode.h:71-97,235,239): BFV tensor
+ * product with the BEHZ full-RNS scaling round(t/q .) (SEAL 2.3 [SEAL-recall], SURVEY.md Appendix
+ * A.6; auxiliary base and m_sk = SEAL's 61-bit internal primes).  n_ct independent pairs:
+ * a [n_ct][size_a][k][n], b [n_ct][size_b][k][n] -> dest [n_ct][size_a + size_b - 1][k][n].
+ * The reference's in-place form `evaluator.multiply(a, b)` is dest -> a afterwards (sizes differ,
+ * so dest must be a separate buffer and must not overlap the operands).  Sizes up to 16.
+ * FHE_ERR_UNSUPPORTED for more than 8 coeff_modulus primes. */
+int fhe_multiply(fhe_ctx *ctx, const uint64_t *a, uint32_t size_a, const uint64_t *b, uint32_t size_b,
+                 uint64_t *dest, uint64_t n_ct);
+/* Evaluator::square(a) (fhe_resize.h:174, fhe_decode.h:67...): same result as multiply(a, a), the
+ * operand is extended and transformed once. */
+int fhe_square(fhe_ctx *ctx, const uint64_t *a, uint32_t size_a, uint64_t *dest, uint64_t n_ct);
+
+/* Evaluator::relinearize(ct, evk) (no call site in homo/; keys at tests/parameters.cpp:89-90,
+ * decomposition_bit_count = DBC fhe_image.h:28).
+ * fhe_evk_create takes the keys of KeyGenerator::generate_evaluation_keys(dbc, count) in
+ * COEFFICIENT form (host): [count][k][digits][2][k][n], key r for s^(2+r), limb i, digit l < digits
+ * = fhe_evk_digits(ctx, dbc) = max_i ceil(bits(q_i) / dbc); the pair encrypts
+ * s^(2+r) 2^(l dbc) in limb i only.  (SEAL stores them NTT-transformed in its own order.) */
+typedef struct fhe_evk fhe_evk;
+uint32_t fhe_evk_digits(const fhe_ctx *ctx, uint32_t dbc);
+int fhe_evk_create(fhe_ctx *ctx, const uint64_t *evk_host, uint32_t dbc, uint32_t count, fhe_evk **out);
+void fhe_evk_destroy(fhe_evk *evk);
+/* a [n_ct][size][k][n] -> dest [n_ct][2][k][n]; needs count >= size - 2; dest must not alias a
+ * unless size == 2. */
+int fhe_relinearize(fhe_ctx *ctx, const uint64_t *a, uint32_t size, const fhe_evk *evk, uint64_t *dest,
+                    uint64_t n_ct);
+
 /* ---- synthetic inputs / checks ---------------------------------------------
  * Counter-based SplitMix64 -> uniform residues, same generator as oracle/fhe_oracle.c. */
 int fhe_fill_uniform(fhe_ctx *ctx, uint64_t *d_dst, uint64_t first_ct, uint64_t n_ct, uint32_t size,

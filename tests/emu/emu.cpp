@@ -11,6 +11,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "../../fully-homomorphic-image-processing_b200/csrc/behz_host.hpp"
 #include "../../fully-homomorphic-image-processing_b200/csrc/dct.cuh"
 #include "../../fully-homomorphic-image-processing_b200/csrc/ntt.cuh"
 #include "../../fully-homomorphic-image-processing_b200/csrc/ring_host.hpp"
@@ -80,7 +81,106 @@ static int inv_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, bool 
     }
 }
 
+template <int LOGN, int LOGE>
+static void emu_fwd_w(const HostBehz &H, int j, const u64 *in, u64 *out)
+{
+    using S = NttShape<LOGN, LOGE>;
+    std::vector<u64> smem(S::SMEM_WORDS), tmp(in, in + S::N);
+    for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 0>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
+    for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 1>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
+    for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 2>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
+}
+template <int LOGN, int LOGE>
+static void emu_inv_w(const HostBehz &H, int j, const u64 *in, u64 *out)
+{
+    using S = NttShape<LOGN, LOGE>;
+    std::vector<u64> smem(S::SMEM_WORDS), tmp(in, in + S::N);
+    for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 2>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
+    for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 1>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
+    for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 0>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
+}
+static int fwd_w_dispatch(const HostBehz &H, int j, const u64 *in, u64 *out)
+{
+    switch (H.dev.logn) {
+    case 10: emu_fwd_w<10, 4>(H, j, in, out); return 0;
+    case 11: emu_fwd_w<11, 4>(H, j, in, out); return 0;
+    case 12: emu_fwd_w<12, 4>(H, j, in, out); return 0;
+    case 13: emu_fwd_w<13, 5>(H, j, in, out); return 0;
+    case 14: emu_fwd_w<14, 5>(H, j, in, out); return 0;
+    default: return -1;
+    }
+}
+static int inv_w_dispatch(const HostBehz &H, int j, const u64 *in, u64 *out)
+{
+    switch (H.dev.logn) {
+    case 10: emu_inv_w<10, 4>(H, j, in, out); return 0;
+    case 11: emu_inv_w<11, 4>(H, j, in, out); return 0;
+    case 12: emu_inv_w<12, 4>(H, j, in, out); return 0;
+    case 13: emu_inv_w<13, 5>(H, j, in, out); return 0;
+    case 14: emu_inv_w<14, 5>(H, j, in, out); return 0;
+    default: return -1;
+    }
+}
+
 extern "C" {
+
+// ---- BEHZ multiply path (csrc/behz.cuh bodies) ----
+void *emu_behz_create(void *ring, char *err, int errlen)
+{
+    auto H = std::make_unique<HostBehz>();
+    std::string e;
+    if (!build_behz(*(HostRing *)ring, *H, e)) {
+        if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
+        return nullptr;
+    }
+    return H.release();
+}
+void emu_behz_destroy(void *h) { delete (HostBehz *)h; }
+uint32_t emu_behz_nb(void *h) { return ((HostBehz *)h)->dev.nb; }
+int emu_nttw_forward(void *h, int j, const uint64_t *in, uint64_t *out) { return fwd_w_dispatch(*(HostBehz *)h, j, (const u64 *)in, (u64 *)out); }
+int emu_nttw_inverse(void *h, int j, const uint64_t *in, uint64_t *out) { return inv_w_dispatch(*(HostBehz *)h, j, (const u64 *)in, (u64 *)out); }
+// x [k][n] -> out [nb][n]
+void emu_behz_extend(void *h, const uint64_t *x, uint64_t *out)
+{
+    const BehzDev &B = ((HostBehz *)h)->dev;
+    for (uint32_t c = 0; c < B.n; ++c) behz_extend_coeff(B, (const u64 *)x + c, B.n, (u64 *)out + c, B.n);
+}
+void emu_behz_scale(void *h, const uint64_t *xq, const uint64_t *xb, uint64_t *out)
+{
+    const BehzDev &B = ((HostBehz *)h)->dev;
+    for (uint32_t c = 0; c < B.n; ++c) behz_scale_coeff(B, (const u64 *)xq + c, B.n, (const u64 *)xb + c, B.n, (u64 *)out + c, B.n);
+}
+// the whole multiply as the library sequences it: extend, forward NTTs, tensor, inverse NTTs, scale
+int emu_multiply(void *ring, void *h, const uint64_t *a1, uint32_t s1, const uint64_t *a2, uint32_t s2, uint64_t *dest)
+{
+    const HostRing &R = *(HostRing *)ring;
+    const HostBehz &H = *(HostBehz *)h;
+    const BehzDev &B = H.dev;
+    const uint32_t n = B.n, k = B.k, nb = B.nb, sd = s1 + s2 - 1;
+    const size_t pq = (size_t)k * n, pb = (size_t)nb * n;
+    std::vector<u64> q1(s1 * pq), b1(s1 * pb), q2(s2 * pq), b2(s2 * pb), dq(sd * pq), db(sd * pb);
+    auto prep = [&](const uint64_t *src, uint32_t s, std::vector<u64> &tq, std::vector<u64> &tb) {
+        for (uint32_t p = 0; p < s; ++p) {
+            emu_behz_extend(h, src + p * pq, (uint64_t *)tb.data() + p * pb);
+            for (uint32_t i = 0; i < k; ++i) fwd_dispatch(R, i, (const u64 *)src + p * pq + (size_t)i * n, tq.data() + p * pq + (size_t)i * n, NTT_OUT_CANON);
+            for (uint32_t j = 0; j < nb; ++j) fwd_w_dispatch(H, j, tb.data() + p * pb + (size_t)j * n, tb.data() + p * pb + (size_t)j * n);
+        }
+    };
+    prep(a1, s1, q1, b1);
+    prep(a2, s2, q2, b2);
+    for (uint32_t i = 0; i < k; ++i)
+        for (uint32_t c = 0; c < n; ++c)
+            behz_tensor_elem(q1.data() + (size_t)i * n + c, q2.data() + (size_t)i * n + c, dq.data() + (size_t)i * n + c, pq, s1, s2, B.q[i], B.qr0[i], B.qr1[i]);
+    for (uint32_t j = 0; j < nb; ++j)
+        for (uint32_t c = 0; c < n; ++c)
+            behz_tensor_elem(b1.data() + (size_t)j * n + c, b2.data() + (size_t)j * n + c, db.data() + (size_t)j * n + c, pb, s1, s2, B.b[j], B.br0[j], B.br1[j]);
+    for (uint32_t p = 0; p < sd; ++p) {
+        for (uint32_t i = 0; i < k; ++i) inv_dispatch(R, i, dq.data() + p * pq + (size_t)i * n, dq.data() + p * pq + (size_t)i * n, true);
+        for (uint32_t j = 0; j < nb; ++j) inv_w_dispatch(H, j, db.data() + p * pb + (size_t)j * n, db.data() + p * pb + (size_t)j * n);
+        emu_behz_scale(h, (const uint64_t *)dq.data() + p * pq, (const uint64_t *)db.data() + p * pb, dest + p * pq);
+    }
+    return 0;
+}
 
 void *emu_ring_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, char *err, int errlen)
 {
