@@ -123,7 +123,7 @@ FHE_HD void behz_scale_coeff(const BehzDev &B, const u64 *xq, size_t qs, const u
 }
 
 // one (limb, position) of the tensor product: d[l] = sum_{x+y=l} a[x] b[y] mod q, operands `stride`
-// words apart per poly, 128-bit accumulation (s1, s2 <= 16 terms of < 2^122), one Barrett reduction
+// words apart per poly, 128-bit accumulation (min(s1, s2) <= 32 terms of < 2^122), one Barrett reduction
 FHE_HD void behz_tensor_elem(const u64 *a, const u64 *b, u64 *d, size_t stride, uint32_t s1, uint32_t s2,
                              u64 q, u64 r0, u64 r1)
 {

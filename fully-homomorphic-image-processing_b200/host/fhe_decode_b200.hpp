@@ -1,0 +1,122 @@
+// fhe_decode_b200.hpp -- the run-length-decode op library of the reference (homo/fhe_decode.h) on
+// B200: the homomorphic Taylor sine / cosine and the Fourier step approximation built on them.
+//
+//   homomorphic_sin (x, res, evaluator, encoder, encryptor)            homo/fhe_decode.h:48-120
+//   homomorphic_cos (x, res, evaluator, encoder, encryptor)            homo/fhe_decode.h:128-200
+//   approximated_step(amplitude, index, count, order, degree, delta, width, height, run,
+//                     evaluator, encoder, encryptor)                    homo/fhe_decode.h:202-242
+//
+// Op for op the reference's graphs, quirks included: both series expand
+// around 3 pi / 2 (:57, :137); `offset` receives add_plain(encode(i)) INSIDE the j loop (:229);
+// the fresh `encrypt(encode(0.0))` each series starts from (:54, :134) comes from the caller's
+// Encryptor.  Without relinearisation the ciphertexts grow: sin / cos return size 11, a step
+// term size 21, each run element size 22.  The decrypting overload of approximated_step
+// (:244-282) needs the SECRET key on the server and is out of scope.
+//
+// `homomorphic_cos` is declared `Ciphertext` in the reference but never returns (:128, UB); here it
+// returns void and delivers the result through `res`, as every caller expects.
+#pragma once
+#include <cmath>
+
+#include "seal_b200.hpp"
+
+namespace seal_b200 {
+
+namespace detail {
+// shared body: the two series differ only in the sign of every coefficient
+inline void taylor_3pi2(Ciphertext &x, Ciphertext &res, double sign, Evaluator &evaluator, FractionalEncoder &encoder,
+                        Encryptor &encryptor)
+{
+    encryptor.encrypt(encoder.encode(0.0), res);
+
+    Ciphertext shifted_x(x);
+    evaluator.add_plain(shifted_x, encoder.encode(-3 * M_PI / 2.0));
+
+    Ciphertext power2(shifted_x);
+    Ciphertext power4(shifted_x);
+    Ciphertext power6(shifted_x);
+    Ciphertext power8(shifted_x);
+    Ciphertext power10(shifted_x);
+
+    // 2nd order term
+    evaluator.square(power2);
+    evaluator.multiply_plain(power2, encoder.encode(sign * 0.5));
+    // 4th order term
+    evaluator.square(power4);
+    evaluator.square(power4);
+    evaluator.multiply_plain(power4, encoder.encode(sign * (-1.0 / 24.0)));
+    // 6th order term
+    evaluator.square(power6);
+    evaluator.square(power6);
+    evaluator.multiply(power6, shifted_x);
+    evaluator.multiply(power6, shifted_x);
+    evaluator.multiply_plain(power6, encoder.encode(sign * (1.0 / 720.0)));
+    // 8th order term
+    evaluator.square(power8);
+    evaluator.square(power8);
+    evaluator.square(power8);
+    evaluator.multiply_plain(power8, encoder.encode(sign * (-1.0 / 40320.0)));
+    // 10th order term
+    evaluator.square(power10);
+    evaluator.square(power10);
+    evaluator.square(power10);
+    evaluator.multiply(power10, shifted_x);
+    evaluator.multiply(power10, shifted_x);
+    evaluator.multiply_plain(power10, encoder.encode(sign * (1.0 / 3628800.0)));
+
+    // 0th order term and the sum
+    evaluator.add_plain(res, encoder.encode(sign * -1.0));
+    evaluator.add(res, power2);
+    evaluator.add(res, power4);
+    evaluator.add(res, power6);
+    evaluator.add(res, power8);
+    evaluator.add(res, power10);
+}
+}  // namespace detail
+
+inline void homomorphic_sin(Ciphertext &x, Ciphertext &res, Evaluator &evaluator, FractionalEncoder &encoder,
+                            Encryptor &encryptor)
+{
+    detail::taylor_3pi2(x, res, 1.0, evaluator, encoder, encryptor);
+}
+inline void homomorphic_cos(Ciphertext &x, Ciphertext &res, Evaluator &evaluator, FractionalEncoder &encoder,
+                            Encryptor &encryptor)
+{
+    detail::taylor_3pi2(x, res, -1.0, evaluator, encoder, encryptor);
+}
+
+inline void approximated_step(Ciphertext &amplitude, Ciphertext &index, Ciphertext &count, int order, int degree,
+                              double delta, int width, int height, std::vector<Ciphertext> &run, Evaluator &evaluator,
+                              FractionalEncoder &encoder, Encryptor &encryptor)
+{
+    Ciphertext b(count);
+    evaluator.multiply_plain(b, encoder.encode(0.5));
+    Ciphertext offset(index);
+    evaluator.add(offset, b);
+    evaluator.add_plain(offset, encoder.encode(-0.5));
+    evaluator.negate(offset);
+    evaluator.add_plain(b, encoder.encode(delta - 0.5));
+    for (int i = 0; i < width * height; i++) {
+        Ciphertext c(b);
+        evaluator.multiply_plain(c, encoder.encode(1.0 / ((double)order)));
+        for (int j = 1; j <= degree; j++) {
+            double arg_factor = ((float)j) * M_PI / ((double)order);
+            Ciphertext sin_arg(b);
+            evaluator.multiply_plain(sin_arg, encoder.encode(arg_factor));
+            Ciphertext cos_arg(offset);
+            evaluator.add_plain(offset, encoder.encode(i));
+            evaluator.multiply_plain(cos_arg, encoder.encode(arg_factor));
+            Ciphertext sin_factor, cos_factor;
+            homomorphic_sin(sin_arg, sin_factor, evaluator, encoder, encryptor);
+            homomorphic_cos(cos_arg, cos_factor, evaluator, encoder, encryptor);
+            Ciphertext term(sin_factor);
+            evaluator.multiply(term, cos_factor);
+            evaluator.multiply_plain(term, encoder.encode(2.0 / (M_PI * ((float)j))));
+            evaluator.add(c, term);
+        }
+        evaluator.multiply(c, amplitude);
+        run.push_back(c);
+    }
+}
+
+}  // namespace seal_b200

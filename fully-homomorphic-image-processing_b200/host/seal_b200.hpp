@@ -18,6 +18,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -223,7 +224,45 @@ inline bool is_contiguous(const std::vector<Ciphertext> &v)
     return true;
 }
 
-class Encryptor {  // passed through by fhe_image.h, never used on the JPEG path
+// seal::Encryptor.  fhe_image.h only passes it through; fhe_resize.h (:230-266) and fhe_decode.h
+// (:54,134) encrypt PUBLIC scalars on the server with it.  Two server-side forms:
+//   * Encryptor(fn): a callback that produces the ciphertext (a real public-key encryption made by
+//     whoever holds the public key -- the parity tests feed the oracle's encryptions through it);
+//   * Encryptor(ctx): the deterministic transparent encryption (Delta*m, 0), which needs no key and
+//     is a valid BFV ciphertext of a public value.
+// A default-constructed Encryptor throws on use, like a seal::Encryptor without a public key.
+class Encryptor {
+public:
+    using Fn = std::function<void(const Plaintext &, Ciphertext &)>;
+    Encryptor() = default;
+    explicit Encryptor(Fn fn) : fn_(std::move(fn)) {}
+    explicit Encryptor(const Context &ctx) : ctx_(&ctx) {}
+    void encrypt(const Plaintext &plain, Ciphertext &destination) const;
+
+private:
+    Fn fn_;
+    const Context *ctx_ = nullptr;
+};
+
+// seal::EvaluationKeys of KeyGenerator::generate_evaluation_keys(dbc, count)
+// (tests/parameters.cpp:89-90), coefficient form [count][k][digits][2][k][n] (include/fhe_b200.h).
+class EvaluationKeys {
+public:
+    EvaluationKeys(const Context &ctx, const uint64_t *keys, uint32_t decomposition_bit_count, uint32_t count)
+        : dbc_(decomposition_bit_count), count_(count)
+    {
+        check(fhe_evk_create(ctx.handle(), keys, dbc_, count_, &h_));
+    }
+    ~EvaluationKeys() { fhe_evk_destroy(h_); }
+    EvaluationKeys(const EvaluationKeys &) = delete;
+    EvaluationKeys &operator=(const EvaluationKeys &) = delete;
+    const fhe_evk *handle() const { return h_; }
+    uint32_t decomposition_bit_count() const { return dbc_; }
+    uint32_t size() const { return count_; }
+
+private:
+    fhe_evk *h_ = nullptr;
+    uint32_t dbc_, count_;
 };
 
 // seal::Evaluator.  Plaintext operands are transformed once and cached by content (the reference
@@ -261,6 +300,33 @@ public:
         require(a);
         check(fhe_sub_plain(ctx_->handle(), a.device_data(), 1, a.size(), table(p), 0));
     }
+    // Evaluator::multiply(a, b): a <- a * b, size a.size() + b.size() - 1 (fhe_resize.h:175-179,
+    // 197-198; fhe_decode.h:71-97,235,239).  BEHZ full-RNS scaling on the device.
+    void multiply(Ciphertext &a, const Ciphertext &b)
+    {
+        require(a);
+        require(b);
+        Ciphertext dest(*ctx_, a.size() + b.size() - 1);
+        check(fhe_multiply(ctx_->handle(), a.device_data(), a.size(), b.device_data(), b.size(), dest.device_data(), 1));
+        a = std::move(dest);
+    }
+    // Evaluator::square(a) (fhe_resize.h:174; fhe_decode.h:67 ...)
+    void square(Ciphertext &a)
+    {
+        require(a);
+        Ciphertext dest(*ctx_, 2 * a.size() - 1);
+        check(fhe_square(ctx_->handle(), a.device_data(), a.size(), dest.device_data(), 1));
+        a = std::move(dest);
+    }
+    // Evaluator::relinearize(a, evk): back to size 2 (north_star; no call site in homo/)
+    void relinearize(Ciphertext &a, const EvaluationKeys &evk)
+    {
+        require(a);
+        if (a.size() <= 2) return;
+        Ciphertext dest(*ctx_, 2);
+        check(fhe_relinearize(ctx_->handle(), a.device_data(), a.size(), evk.handle(), dest.device_data(), 1));
+        a = std::move(dest);
+    }
     const Context &context() const { return *ctx_; }
     // per-evaluator cache slot for the fused-graph plans of fhe_image_b200.hpp
     std::shared_ptr<void> &plan_slot(const std::string &key) { return plans_[key]; }
@@ -275,9 +341,19 @@ private:
     {
         require(a);
         require(b);
-        // SEAL allows unequal sizes (result = max); the JPEG path only ever meets size 2.
-        if (a.size() != b.size()) throw std::invalid_argument("ciphertext sizes differ (not needed by fhe_image.h)");
-        check(fn(ctx_->handle(), a.device_data(), b.device_data(), 1, a.size()));
+        // SEAL allows unequal sizes: the result has the larger size, missing polynomials count as
+        // zero (fhe_resize.h:182-185 adds sizes 4, 3 and 2).
+        if (b.size() > a.size()) {
+            const size_t wa = ctx_->ct_words(a.size()), wb = ctx_->ct_words(b.size());
+            Ciphertext r(*ctx_, b.size());
+            check(fhe_device_copy(ctx_->handle(), r.device_data(), a.device_data(), wa * sizeof(uint64_t)));
+            check(fhe_device_copy(ctx_->handle(), r.device_data() + wa, b.device_data() + wa, (wb - wa) * sizeof(uint64_t)));
+            if ((void *)fn == (void *)fhe_sub) check(fhe_negate(ctx_->handle(), r.device_data() + wa, 1, b.size() - a.size()));
+            check(fn(ctx_->handle(), r.device_data(), b.device_data(), 1, a.size()));
+            a = std::move(r);
+            return;
+        }
+        check(fn(ctx_->handle(), a.device_data(), b.device_data(), 1, b.size()));
     }
     fhe_ptab *table(const Plaintext &p)
     {
@@ -294,5 +370,25 @@ private:
     std::unordered_map<std::string, fhe_ptab *> cache_;
     std::unordered_map<std::string, std::shared_ptr<void>> plans_;
 };
+
+inline void Encryptor::encrypt(const Plaintext &plain, Ciphertext &destination) const
+{
+    if (fn_) {
+        fn_(plain, destination);
+        return;
+    }
+    if (!ctx_) throw std::logic_error("this Encryptor holds no public key and no context");
+    if (plain.coeffs().size() != ctx_->poly_degree()) throw std::invalid_argument("plain is not valid for encryption parameters");
+    Ciphertext z(*ctx_, 2);
+    check(fhe_device_zero(ctx_->handle(), z.device_data(), ctx_->ct_words(2) * sizeof(uint64_t)));
+    if (!plain.is_zero()) {
+        fhe_ptab *t = nullptr;
+        check(fhe_ptab_create(ctx_->handle(), plain.coeffs().data(), 1, &t));
+        const int rc = fhe_add_plain(ctx_->handle(), z.device_data(), 1, 2, t, 0);
+        fhe_ptab_destroy(t);
+        check(rc);
+    }
+    destination = std::move(z);
+}
 
 }  // namespace seal_b200

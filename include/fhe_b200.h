@@ -130,13 +130,19 @@ int fhe_dct8x8_quantize(fhe_ctx *ctx, const fhe_dct_plan *plan, const uint64_t *
 int fhe_dct8x8_quantize_host(fhe_ctx *ctx, const fhe_dct_plan *plan, const uint64_t *h_in,
                              uint64_t *h_out, uint64_t nblocks);
 
+/* All-zero ciphertext storage on the context's stream: the transparent encryption of 0 that the
+ * deterministic server-side Encryptor starts from (fhe_resize.h:230-266 and fhe_decode.h:54,134
+ * encrypt public scalars on the server). */
+int fhe_device_zero(fhe_ctx *ctx, void *dptr, size_t bytes);
+
 /* ---- Evaluator: ciphertext x ciphertext ----------------------------------------------------
  * Evaluator::multiply(a, b) (fhe_resize.h:175-179,197-198; fhe_decode.h:71-97,235,239): BFV tensor
  * product with the BEHZ full-RNS scaling round(t/q .) (SEAL 2.3 [SEAL-recall], SURVEY.md Appendix
  * A.6; auxiliary base and m_sk = SEAL's 61-bit internal primes).  n_ct independent pairs:
  * a [n_ct][size_a][k][n], b [n_ct][size_b][k][n] -> dest [n_ct][size_a + size_b - 1][k][n].
  * The reference's in-place form `evaluator.multiply(a, b)` is dest -> a afterwards (sizes differ,
- * so dest must be a separate buffer and must not overlap the operands).  Sizes up to 16.
+ * so dest must be a separate buffer and must not overlap the operands).  Sizes up to 32
+ * (the decode graph reaches 21 x 2, fhe_decode.h:239).
  * FHE_ERR_UNSUPPORTED for more than 8 coeff_modulus primes. */
 int fhe_multiply(fhe_ctx *ctx, const uint64_t *a, uint32_t size_a, const uint64_t *b, uint32_t size_b,
                  uint64_t *dest, uint64_t n_ct);

@@ -1,0 +1,137 @@
+// test_resize_decode.cpp -- the C++ host layer for the resize and decode op libraries
+// (host/fhe_resize_b200.hpp, host/fhe_decode_b200.hpp) on a real B200.
+//
+// Usage: test_resize_decode <n> <in.bin> <out.bin>
+// in.bin (raw u64, size-2 ciphertexts of W = 2*k*n words, written by tests/test_host_cpp.py from
+// the oracle's generator / encryptor):
+//   [0..4]   A B C D t            -> Cubic level 1 (size 4), Cubic level 2 on four copies (size 6),
+//                                    Linear(A, B, t) (size 3)
+//   [5..7]   amplitude index count
+//   [8..15]  8 fresh "encryptions of zero" consumed by sin/cos inside approximated_step
+//            (order 8, degree 2, delta 0.25, width*height 2); [8],[9] also feed the stand-alone
+//            homomorphic_sin(A) / homomorphic_cos(B)
+//   [16..33] 18 encrypted fractions, consumed in call order by SampleBicubic (2 per output pixel)
+//   [34..]   5x6 RGB source image, RGB-interleaved row-major (90 ciphertexts)
+// out.bin: the results in the order above, then the 3x3 bicubic ResizeImage output (9 pixels x 3
+// channels, size 6).  The pytest wrapper compares it with the oracle bit for bit.
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+
+#include "../../fully-homomorphic-image-processing_b200/host/fhe_decode_b200.hpp"
+#include "../../fully-homomorphic-image-processing_b200/host/fhe_resize_b200.hpp"
+
+using namespace seal_b200;
+
+#define REQUIRE(cond)                                                            \
+    do {                                                                         \
+        if (!(cond)) {                                                           \
+            std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            return 1;                                                            \
+        }                                                                        \
+    } while (0)
+
+int main(int argc, char **argv)
+{
+    try {
+        const uint32_t n = argc > 1 ? (uint32_t)std::atoi(argv[1]) : 2048;
+        Context ctx(n);
+        if (argc < 4) {
+            std::fprintf(stderr, "usage: %s n in.bin out.bin\n", argv[0]);
+            return 2;
+        }
+        const size_t W = ctx.ct_words(2);
+        std::ifstream in(argv[2], std::ios::binary);
+        REQUIRE((bool)in);
+        in.seekg(0, std::ios::end);
+        const size_t bytes = (size_t)in.tellg();
+        in.seekg(0);
+        std::vector<uint64_t> words(bytes / 8);
+        in.read((char *)words.data(), (std::streamsize)bytes);
+        REQUIRE(words.size() >= (34 + 90) * W);
+        auto ct_at = [&](size_t i) {
+            Ciphertext c(ctx, 2);
+            c.upload(words.data() + i * W);
+            return c;
+        };
+        std::ofstream out(argv[3], std::ios::binary);
+        auto dump = [&](const Ciphertext &c) {
+            std::vector<uint64_t> h(ctx.ct_words(c.size()));
+            c.download(h.data());
+            out.write((const char *)h.data(), (std::streamsize)(h.size() * 8));
+        };
+        // the functions print timings like the reference; keep stdout clean (restored on every path)
+        struct Quiet {
+            std::ostringstream sink;
+            std::streambuf *old;
+            Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
+            ~Quiet() { std::cout.rdbuf(old); }
+        } quiet;
+
+        Evaluator evaluator(ctx);
+        FractionalEncoder encoder(ctx, 64, 32);
+        size_t next_zero = 8, next_frac = 16;
+        Encryptor zeros([&](const Plaintext &, Ciphertext &dst) { dst = ct_at(next_zero++); });
+        Encryptor fracs([&](const Plaintext &, Ciphertext &dst) { dst = ct_at(next_frac++); });
+
+        Ciphertext A = ct_at(0), B = ct_at(1), C = ct_at(2), D = ct_at(3), t = ct_at(4);
+        Ciphertext c1, c2, lin;
+        Cubic(c1, A, B, C, D, t, evaluator, encoder, zeros);
+        REQUIRE(c1.size() == 4);
+        dump(c1);
+        Ciphertext e1(c1), e2(c1), e3(c1), e4(c1);
+        Cubic(c2, e1, e2, e3, e4, t, evaluator, encoder, zeros);
+        REQUIRE(c2.size() == 6);
+        dump(c2);
+        Linear(lin, A, B, t, evaluator, encoder, zeros);
+        REQUIRE(lin.size() == 3);
+        dump(lin);
+
+        Ciphertext s, c;
+        homomorphic_sin(A, s, evaluator, encoder, zeros);
+        homomorphic_cos(B, c, evaluator, encoder, zeros);
+        REQUIRE(s.size() == 11 && c.size() == 11 && next_zero == 10);
+        dump(s);
+        dump(c);
+
+        next_zero = 8;
+        Ciphertext amplitude = ct_at(5), index = ct_at(6), count = ct_at(7);
+        std::vector<Ciphertext> run;
+        approximated_step(amplitude, index, count, 8, 2, 0.25, 2, 1, run, evaluator, encoder, zeros);
+        REQUIRE(run.size() == 2 && run[0].size() == 22 && next_zero == 16);
+        dump(run[0]);
+        dump(run[1]);
+
+        size_t next_src = 34;
+        SImageData dest;
+        ResizeImage([&](Ciphertext &dst) { dst = ct_at(next_src++); }, 5, 6, dest, 3, 3, BICUBIC, evaluator, encoder, fracs);
+        REQUIRE(dest.pixels.size() == 9 && next_frac == 34 && next_src == 34 + 90);
+        for (auto &px : dest.pixels)
+            for (auto &ch : px) {
+                REQUIRE(ch.size() == 6);
+                dump(ch);
+            }
+
+        // the key-less deterministic Encryptor: (Delta*m, 0) decrypts to m and is accepted by the graphs
+        Encryptor transparent(ctx);
+        Ciphertext tz;
+        transparent.encrypt(encoder.encode(0.375), tz);
+        REQUIRE(tz.size() == 2);
+        dump(tz);
+        // a default-constructed Encryptor has no key: std::logic_error
+        bool threw = false;
+        try {
+            Encryptor none;
+            none.encrypt(encoder.encode(1.0), tz);
+        } catch (const std::logic_error &) {
+            threw = true;
+        }
+        REQUIRE(threw);
+        std::printf("PASS\n");
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "exception: %s\n", e.what());
+        return 1;
+    }
+}
