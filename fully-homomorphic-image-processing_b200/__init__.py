@@ -46,7 +46,8 @@ def build(force: bool = False) -> str:
     """Compile csrc/ for sm_100a into the in-tree libfhe_b200.so (nvcc cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc", "fhe_b200.cu")
     deps = [src] + [os.path.join(_HERE, "csrc", f) for f in (
-        "ntt.cuh", "dct.cuh", "modarith.cuh", "ring_host.hpp", "ntt_wide.cuh", "behz.cuh", "behz_host.hpp", "behz_api.inc")]
+        "ntt.cuh", "dct.cuh", "modarith.cuh", "ring_host.hpp", "ntt_wide.cuh", "behz.cuh", "behz_host.hpp", "behz_api.inc",
+        "jpeg_api.inc")]
     deps.append(os.path.join(ROOT, "include", "fhe_b200.h"))
     stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if force or stale:
@@ -102,6 +103,9 @@ def lib():
         "fhe_set_dct_chunk_blocks": (i32, [vp, u32]),
         "fhe_set_stage_timing": (i32, [vp, i32]),
         "fhe_get_stage_times": (i32, [vp, C.POINTER(C.c_float)]),
+        "fhe_jpeg_plan_create": (i32, [vp, u64p, u64p, u64p, u64p, u64p, u64p, C.POINTER(vp)]),
+        "fhe_jpeg_plan_destroy": (None, [vp]),
+        "fhe_jpeg_rgb_tiles": (i32, [vp, vp, vp, vp, u64]),
         "fhe_device_zero": (i32, [vp, vp, C.c_size_t]),
         "fhe_multiply": (i32, [vp, vp, u32, vp, u32, vp, u64]),
         "fhe_square": (i32, [vp, vp, u32, vp, u64]),
@@ -125,7 +129,7 @@ EXPORTED_SYMBOLS = (
     "fhe_ntt_forward", "fhe_ntt_inverse", "fhe_dct_plan_create", "fhe_dct_plan_destroy",
     "fhe_dct8x8_quantize", "fhe_dct8x8_quantize_host", "fhe_fill_uniform", "fhe_checksum",
     "fhe_launch_count", "fhe_set_dct_chunk_blocks", "fhe_set_stage_timing", "fhe_get_stage_times",
-    "fhe_device_zero", "fhe_multiply", "fhe_square", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
+    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_multiply", "fhe_square", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
 )
 
 
@@ -333,6 +337,45 @@ class DctPlan:
             self.close()
         except Exception:
             pass
+
+
+# fhe_image.h:317-319 -- the plaintexts rgb_to_ycc_fhe encodes, in call order
+COLOR_CONSTANTS = (0.299, 0.587, 0.114, -0.168736, 0.331264, 0.5, 0.5, 0.418688, 0.081312)
+
+
+class JpegPlan:
+    """Tables of the whole server_jpeg tile step (server_jpeg.cpp:126-135): rgb_to_ycc_fhe +
+    encrypted_dct per channel (+ quantize_fhe with `quant_y` / `quant_c` when given)."""
+
+    def __init__(self, ctx: Context, encoder: FractionalEncoder, quant_y=None, quant_c=None):
+        import numpy as np
+        color = np.stack([encoder.encode(c) for c in COLOR_CONSTANTS])
+        off = encoder.encode(128.0)
+        consts = np.stack([encoder.encode(c) for c in DCT_CONSTANTS])
+        eighth = encoder.encode(0.125)
+        qy = np.stack([encoder.encode(1 / float(v)) for v in quant_y]) if quant_y is not None else None
+        qc = np.stack([encoder.encode(1 / float(v)) for v in quant_c]) if quant_c is not None else None
+        h = C.c_void_p()
+        _check(lib().fhe_jpeg_plan_create(ctx.h, _np_ptr(color), _np_ptr(off), _np_ptr(consts), _np_ptr(eighth),
+                                          _np_ptr(qy) if qy is not None else None,
+                                          _np_ptr(qc) if qc is not None else None, C.byref(h)))
+        self.h, self.ctx = h, ctx
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().fhe_jpeg_plan_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def jpeg_rgb_tiles(ctx: Context, plan: JpegPlan, d_in: int, d_out: int, ntiles: int):
+    """rgb_to_ycc_fhe + encrypted_dct (+ quantize_fhe) on device tiles [tile][3][64][2][k][n]."""
+    _check(lib().fhe_jpeg_rgb_tiles(ctx.h, plan.h, C.c_void_p(d_in), C.c_void_p(d_out), ntiles))
 
 
 def encrypted_dct_quantize(ctx: Context, plan: DctPlan, d_in: int, d_out: int, nblocks: int):

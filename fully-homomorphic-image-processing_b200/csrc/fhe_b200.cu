@@ -121,7 +121,7 @@ k_mulplain(const u64 *in, u64 *out, const W2 *__restrict__ table, RingDev R)
 // on B200, and a 3-CTA/SM register cap spills: profiles/r01_notes.md.)
 __global__ void __launch_bounds__(256, 2)
 k_dct_pointwise(u64 *data, const W2 *__restrict__ ctab, const W2 *__restrict__ stab, RingDev R,
-                unsigned long long nunits, int upc)
+                unsigned long long nunits, int upc, uint32_t blk_stride /* ciphertexts between blocks: 64 = dense */)
 {
     __shared__ u64 sbuf[2][64 * DCT_TILE];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -141,7 +141,7 @@ k_dct_pointwise(u64 *data, const W2 *__restrict__ ctab, const W2 *__restrict__ s
         if (u >= nunits) break;
         const unsigned long long blk = u >> 1;
         const uint32_t poly = (uint32_t)(u & 1);
-        u64 *base = data + blk * 64 * ct_stride + ((size_t)poly * k + j) * n + (size_t)tile * DCT_TILE;
+        u64 *base = data + blk * blk_stride * ct_stride + ((size_t)poly * k + j) * n + (size_t)tile * DCT_TILE;
         u64 *sb = sbuf[it & 1];
         dct_row_phase(w, lane, base, ct_stride, sb, c, q, n2q);
         __syncthreads();
@@ -826,7 +826,7 @@ static int dct_chunk(fhe_ctx *c, const fhe_dct_plan *plan, const u64 *in, u64 *o
     const unsigned long long ugs = (nunits + upc - 1) / upc;
     const unsigned long long grid = ugs * k * (n / DCT_TILE);
     if (grid > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many blocks in one chunk");
-    k_dct_pointwise<<<(unsigned)grid, 256, 0, st>>>(out, plan->d_c, plan->d_s, c->dev, nunits, upc);
+    k_dct_pointwise<<<(unsigned)grid, 256, 0, st>>>(out, plan->d_c, plan->d_s, c->dev, nunits, upc, 64);
     c->launches++;
     CU_TRY(cudaGetLastError());
     if (int rc = mark()) return rc;
@@ -924,3 +924,4 @@ int fhe_checksum(fhe_ctx *c, const uint64_t *d, uint64_t count, uint64_t *out)
 }  // extern "C"
 
 #include "behz_api.inc"
+#include "jpeg_api.inc"

@@ -130,6 +130,26 @@ int fhe_dct8x8_quantize(fhe_ctx *ctx, const fhe_dct_plan *plan, const uint64_t *
 int fhe_dct8x8_quantize_host(fhe_ctx *ctx, const fhe_dct_plan *plan, const uint64_t *h_in,
                              uint64_t *h_out, uint64_t nblocks);
 
+/* ---- the whole server_jpeg tile step -------------------------------------------------------
+ * server_jpeg.cpp:113-138 per 8x8 RGB tile: rgb_to_ycc_fhe on the 64 pixels (fhe_image.h:310-325:
+ * Y = .299 R + .587 G + .114 B - 128, Cb = -.168736 R - .331264 G + .5 B,
+ * Cr = .5 R - .418688 G - .081312 B) then encrypted_dct of Y, Cb, Cr (:196-288) [then quantize_fhe
+ * (:294-305) when tables are given], fused: one forward NTT kernel with the colour conversion in
+ * its epilogue, the pointwise DCT per channel, one inverse NTT kernel.
+ * color_consts [9][n]: encode() of 0.299, 0.587, 0.114, -0.168736, 0.331264, 0.5, 0.5, 0.418688,
+ * 0.081312 in this order (the reference subtracts the terms it encodes positively, :318-319);
+ * offset128 [n] = encode(128.0); dct_consts / eighth as in fhe_dct_plan_create; quant_y / quant_c:
+ * [64][n] encode(1/quant[i]) for Y and for Cb/Cr, or NULL (server_jpeg.cpp itself never quantises).
+ * Tiles: [tile][3][64][2][k][n] -- R64, G64, B64 in (server_jpeg.cpp:115-124), Y64, Cb64, Cr64 out
+ * (:146-153); d_in may equal d_out. */
+typedef struct fhe_jpeg_plan fhe_jpeg_plan;
+int fhe_jpeg_plan_create(fhe_ctx *ctx, const uint64_t *color_consts, const uint64_t *offset128,
+                         const uint64_t *dct_consts, const uint64_t *eighth, const uint64_t *quant_y,
+                         const uint64_t *quant_c, fhe_jpeg_plan **out);
+void fhe_jpeg_plan_destroy(fhe_jpeg_plan *plan);
+int fhe_jpeg_rgb_tiles(fhe_ctx *ctx, const fhe_jpeg_plan *plan, const uint64_t *d_in, uint64_t *d_out,
+                       uint64_t ntiles);
+
 /* All-zero ciphertext storage on the context's stream: the transparent encryption of 0 that the
  * deterministic server-side Encryptor starts from (fhe_resize.h:230-266 and fhe_decode.h:54,134
  * encrypt public scalars on the server). */
