@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--e2e-blocks", type=int, default=256, help="blocks per end-to-end step (host buffers)")
     ap.add_argument("--chunk", type=int, default=0, help="internal chunk blocks (0 = one chunk)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-tile", action="store_true", help="skip the fused RGB-tile side measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -221,6 +222,26 @@ def main():
     if world > 1:
         dist.all_reduce(cs_t, op=dist.ReduceOp.BXOR)
 
+    # ---- side measurement (not the headline): the whole server_jpeg tile step, colour conversion
+    # fused into the forward NTT (fhe_jpeg_rgb_tiles), in place on the same resident buffer ------
+    tile_info = None
+    if not args.no_tile:
+        jplan = pkg.JpegPlan(ctx, enc, pkg.YQT, pkg.UVQT)
+        ntiles = B // 3
+        for _ in range(2):
+            pkg.jpeg_rgb_tiles(ctx, jplan, d_in.data_ptr(), d_in.data_ptr(), ntiles)
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record(stream)
+        for _ in range(3):
+            pkg.jpeg_rgb_tiles(ctx, jplan, d_in.data_ptr(), d_in.data_ptr(), ntiles)
+        t1e.record(stream)
+        torch.cuda.synchronize()
+        tms = t0e.elapsed_time(t1e) / 3
+        tile_info = {"what": "rgb_to_ycc_fhe + encrypted_dct + quantize_fhe per 8x8 RGB tile (3 channel blocks), "
+                             "fused, per GPU", "tiles_per_s": ntiles / (tms * 1e-3),
+                     "channel_blocks_per_s": 3 * ntiles / (tms * 1e-3), "ms": tms, "tiles": ntiles}
+        jplan.close()
+
     # ---- end to end through the C-ABI with HOST (pinned) buffers, copies inside the call -------
     del d_in, d_out
     torch.cuda.empty_cache()
@@ -257,7 +278,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get(names[dom])
+            # dram__bytes_read.sum + dram__bytes_write.sum of one ncu capture, stored per block
+            traffic = json.load(f)["per_block_bytes"][names[dom]] * B
     except Exception:
         pass
     roofline = {"bound": "hbm", "kernel": names[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -290,7 +312,7 @@ def main():
             "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ebytes, "d2h_bytes_per_step": ebytes,
                     "blocks_per_step": EB, "steps": e2e_steps},
-            "roofline": roofline, "cpu_baseline": cpu,
+            "roofline": roofline, "cpu_baseline": cpu, "server_jpeg_tile": tile_info,
             "output_checksum_xor": hex(int(cs_t.item())),
         }))
     plan.close()
