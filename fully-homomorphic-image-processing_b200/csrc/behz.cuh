@@ -57,14 +57,21 @@ FHE_HD u64 mulsh_canon(u64 x, W2 c, u64 q) { return csub(mulsh(x, c, q), q); }
 // ---------------------------------------------------------------------------------------------
 // per-coefficient bodies (host + device: tests/emu runs them on the CPU)
 // ---------------------------------------------------------------------------------------------
+// Both bodies are templates on the base sizes: K = |q| and KB = |B| known at compile time (K > 0:
+// every loop unrolls, the residues live in registers) or taken from BehzDev at run time (K == 0).
+//
 // x: this coefficient's k residues (stride xs); out: nb residues (stride os)
-FHE_HD void behz_extend_coeff(const BehzDev &B, const u64 *x, size_t xs, u64 *out, size_t os)
+template <int K, int KB>
+FHE_HD void behz_extend_coeff_t(const BehzDev &B, const u64 *x, size_t xs, u64 *out, size_t os)
 {
-    u64 y[BEHZ_MAXK];
+    constexpr bool ST = K > 0;
+    constexpr int MK = ST ? K : BEHZ_MAXK, MB = ST ? KB + 1 : BEHZ_MAXB;
+    const int k = ST ? K : (int)B.k, nb = ST ? KB + 1 : (int)B.nb;
+    u64 y[MK];
     u32 vm = 0;
 #pragma unroll
-    for (int i = 0; i < BEHZ_MAXK; ++i)
-        if (i < (int)B.k) {
+    for (int i = 0; i < MK; ++i)
+        if (ST || i < k) {
             y[i] = mulsh_canon(x[i * xs], B.mt_qhat_inv[i], B.q[i]);
             vm += (u32)y[i] * B.qhat_mod_mt[i];
         }
@@ -72,38 +79,47 @@ FHE_HD void behz_extend_coeff(const BehzDev &B, const u64 *x, size_t xs, u64 *ou
     const u32 r = vm * B.neg_inv_q_mod_mt;
     const bool neg = r >= 0x80000000u;
     const u64 rabs = neg ? (u64)(0u - r) : (u64)r;
-    for (uint32_t j = 0; j < B.nb; ++j) {
-        u128d acc = (u128d)rabs * (neg ? B.Dneg[j] : B.Dpos[j]);
 #pragma unroll
-        for (int i = 0; i < BEHZ_MAXK; ++i)
-            if (i < (int)B.k) acc += (u128d)y[i] * B.C[j][i];
-        out[j * os] = barrett_u128(acc, B.b[j], B.br0[j], B.br1[j]);
-    }
+    for (int j = 0; j < MB; ++j)
+        if (ST || j < nb) {
+            u128d acc = (u128d)rabs * (neg ? B.Dneg[j] : B.Dpos[j]);
+#pragma unroll
+            for (int i = 0; i < MK; ++i)
+                if (ST || i < k) acc += (u128d)y[i] * B.C[j][i];
+            out[j * os] = barrett_u128(acc, B.b[j], B.br0[j], B.br1[j]);
+        }
 }
 
 // xq: k residues of the tensor result in base q, xb: nb residues in base B_sk; out: k residues
-FHE_HD void behz_scale_coeff(const BehzDev &B, const u64 *xq, size_t qs, const u64 *xb, size_t bs, u64 *out, size_t os)
+template <int K, int KB>
+FHE_HD void behz_scale_coeff_t(const BehzDev &B, const u64 *xq, size_t qs, const u64 *xb, size_t bs, u64 *out, size_t os)
 {
-    u64 y[BEHZ_MAXK], f[BEHZ_MAXB], z[BEHZ_MAXB];
+    constexpr bool ST = K > 0;
+    constexpr int MK = ST ? K : BEHZ_MAXK, MB = ST ? KB + 1 : BEHZ_MAXB;
+    const int k = ST ? K : (int)B.k, kb = ST ? KB : (int)B.kb, nb = kb + 1;
+    u64 y[MK], f[MB], z[MB];
 #pragma unroll
-    for (int i = 0; i < BEHZ_MAXK; ++i)
-        if (i < (int)B.k) y[i] = mulsh_canon(xq[i * qs], B.T[i], B.q[i]);
+    for (int i = 0; i < MK; ++i)
+        if (ST || i < k) y[i] = mulsh_canon(xq[i * qs], B.T[i], B.q[i]);
     // fast_floor: (t x_bsk - conv(t x_q)) q^-1 mod b_j
 #pragma unroll
-    for (int j = 0; j < BEHZ_MAXB; ++j)
-        if (j < (int)B.nb) {
+    for (int j = 0; j < MB; ++j)
+        if (ST || j < nb) {
             u128d acc = (u128d)xb[j * bs] * B.E[j];
 #pragma unroll
-            for (int i = 0; i < BEHZ_MAXK; ++i)
-                if (i < (int)B.k) acc += (u128d)y[i] * B.F[j][i];
+            for (int i = 0; i < MK; ++i)
+                if (ST || i < k) acc += (u128d)y[i] * B.F[j][i];
             f[j] = barrett_u128(acc, B.b[j], B.br0[j], B.br1[j]);
         }
     // fastbconv_sk: alpha = [(conv_B->msk(f) - f_sk) B^-1] mod m_sk, centred
-    const uint32_t kb = B.kb;
-    u128d acc = (u128d)f[kb] * B.H;
+    u64 fsk = 0;
 #pragma unroll
-    for (int l = 0; l < BEHZ_MAXB; ++l)
-        if (l < (int)kb) {
+    for (int j = 0; j < MB; ++j)
+        if (j == kb) fsk = f[j];
+    u128d acc = (u128d)fsk * B.H;
+#pragma unroll
+    for (int l = 0; l < MB; ++l)
+        if (l < kb) {
             z[l] = mulsh_canon(f[l], B.bhat_inv[l], B.b[l]);
             acc += (u128d)z[l] * B.G[l];
         }
@@ -112,14 +128,23 @@ FHE_HD void behz_scale_coeff(const BehzDev &B, const u64 *xq, size_t qs, const u
     const bool neg = alpha > (msk >> 1);
     const u64 aabs = neg ? msk - alpha : alpha;
 #pragma unroll
-    for (int i = 0; i < BEHZ_MAXK; ++i)
-        if (i < (int)B.k) {
+    for (int i = 0; i < MK; ++i)
+        if (ST || i < k) {
             u128d a2 = (u128d)aabs * (neg ? B.Bq_pos[i] : B.Bq_neg[i]);
 #pragma unroll
-            for (int l = 0; l < BEHZ_MAXB; ++l)
-                if (l < (int)kb) a2 += (u128d)z[l] * B.I[i][l];
+            for (int l = 0; l < MB; ++l)
+                if (l < kb) a2 += (u128d)z[l] * B.I[i][l];
             out[i * os] = barrett_u128(a2, B.q[i], B.qr0[i], B.qr1[i]);
         }
+}
+// run-time sizes (tests/emu, unusual bases)
+FHE_HD void behz_extend_coeff(const BehzDev &B, const u64 *x, size_t xs, u64 *out, size_t os)
+{
+    behz_extend_coeff_t<0, 0>(B, x, xs, out, os);
+}
+FHE_HD void behz_scale_coeff(const BehzDev &B, const u64 *xq, size_t qs, const u64 *xb, size_t bs, u64 *out, size_t os)
+{
+    behz_scale_coeff_t<0, 0>(B, xq, qs, xb, bs, out, os);
 }
 
 // one (limb, position) of the tensor product: d[l] = sum_{x+y=l} a[x] b[y] mod q, operands `stride`
@@ -140,31 +165,33 @@ FHE_HD void behz_tensor_elem(const u64 *a, const u64 *b, u64 *d, size_t stride, 
 // ---------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------
+// The constants travel as a __grid_constant__ kernel parameter (3.3 KB): every read is a uniform
+// constant-bank access instead of a global load.
 // polys: [npoly][k][n] -> ext: [npoly][nb][n]
+template <int K, int KB>
 __global__ void __launch_bounds__(256) k_behz_extend(const u64 *__restrict__ x, u64 *__restrict__ ext,
-                                                      unsigned long long npoly, const BehzDev *__restrict__ Bp)
+                                                      unsigned long long npoly, const __grid_constant__ BehzDev B)
 {
-    const BehzDev &B = *Bp;
     const unsigned long long total = npoly << B.logn;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long p = i >> B.logn;
         const uint32_t c = (uint32_t)(i & (B.n - 1));
-        behz_extend_coeff(B, x + p * B.k * B.n + c, B.n, ext + p * B.nb * B.n + c, B.n);
+        behz_extend_coeff_t<K, KB>(B, x + p * B.k * B.n + c, B.n, ext + p * B.nb * B.n + c, B.n);
     }
 }
 // dq: [npoly][k][n], db: [npoly][nb][n] -> out: [npoly][k][n]
+template <int K, int KB>
 __global__ void __launch_bounds__(256) k_behz_scale(const u64 *__restrict__ dq, const u64 *__restrict__ db,
                                                      u64 *__restrict__ out, unsigned long long npoly,
-                                                     const BehzDev *__restrict__ Bp)
+                                                     const __grid_constant__ BehzDev B)
 {
-    const BehzDev &B = *Bp;
     const unsigned long long total = npoly << B.logn;
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long p = i >> B.logn;
         const uint32_t c = (uint32_t)(i & (B.n - 1));
-        behz_scale_coeff(B, dq + p * B.k * B.n + c, B.n, db + p * B.nb * B.n + c, B.n, out + p * B.k * B.n + c, B.n);
+        behz_scale_coeff_t<K, KB>(B, dq + p * B.k * B.n + c, B.n, db + p * B.nb * B.n + c, B.n, out + p * B.k * B.n + c, B.n);
     }
 }
 

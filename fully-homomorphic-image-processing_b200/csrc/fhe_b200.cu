@@ -858,8 +858,9 @@ int fhe_dct8x8_quantize_host(fhe_ctx *c, const fhe_dct_plan *plan, const uint64_
     if (!nblocks) return FHE_OK;
     clear_stage_events(c);
     const size_t blk_bytes = (size_t)64 * 2 * c->host.k * c->host.n * sizeof(u64);
-    // staging slots of up to 256 MiB
-    uint64_t sb = (256ull << 20) / blk_bytes;
+    // staging slots of up to 64 MiB: the copies bound this path (PCIe), so small slots keep the
+    // pipeline's fill and drain (one H2D and one D2H that overlap nothing) short
+    uint64_t sb = (64ull << 20) / blk_bytes;
     if (sb < 1) sb = 1;
     if (sb > nblocks) sb = nblocks;
     if (c->stage_blocks < sb) {
