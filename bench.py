@@ -28,6 +28,8 @@ sys.path.insert(0, ROOT)
 N_RING, T_PLAIN = 4096, 1 << 14
 IMAGE_BLOCKS = 3 * 16384  # 1024x1024 RGB
 METRIC = "encrypted 8x8 DCT+quantize blocks/sec"
+WORKLOAD = ("server_jpeg DCT+quantize, 1024x1024 RGB (3x16384 blocks), n=4096 k=2 t=2^14, "
+            "streamed as HBM-resident chunks")
 UNIT = "blocks/s"
 
 
@@ -122,8 +124,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": "server_jpeg DCT+quantize 1024x1024 RGB, n=4096 k=2 t=2^14 (bounded CPU sample)",
-                   "blocks_per_step": blocks},
+        "config": {"workload": WORKLOAD, "blocks_per_step": blocks, "image_blocks": IMAGE_BLOCKS,
+                   "note": "bounded CPU sample of the same workload on the host cores"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -220,7 +222,13 @@ def main():
     cs = ctx.checksum(d_out.data_ptr(), words)
     cs_t = torch.tensor([cs & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
     if world > 1:
-        dist.all_reduce(cs_t, op=dist.ReduceOp.BXOR)
+        # NCCL has no XOR reduction: gather the per-rank checksums and fold them on the host
+        allcs = torch.empty(world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allcs, cs_t)
+        folded = 0
+        for v in allcs.tolist():
+            folded ^= int(v)
+        cs_t = torch.tensor([folded], dtype=torch.int64, device="cuda")
 
     # ---- side measurement (not the headline): the whole server_jpeg tile step, colour conversion
     # fused into the forward NTT (fhe_jpeg_rgb_tiles), in place on the same resident buffer ------
@@ -304,8 +312,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "server_jpeg DCT+quantize, 1024x1024 RGB (3x16384 blocks), n=4096 k=2 t=2^14, "
-                                   "streamed as HBM-resident chunks",
+            "config": {"workload": WORKLOAD,
                        "blocks_per_step_per_gpu": B, "image_blocks": IMAGE_BLOCKS,
                        "l2": "inputs larger than L2 (no flush needed)", "parallelism": f"blocks sharded x{world}",
                        "internal_chunk_blocks": args.chunk},
