@@ -82,6 +82,7 @@ def lib():
         "fhe_upload": (i32, [vp, vp, vp, C.c_size_t]),
         "fhe_download": (i32, [vp, vp, vp, C.c_size_t]),
         "fhe_device_copy": (i32, [vp, vp, vp, C.c_size_t]),
+        "fhe_device_copy_2d": (i32, [vp, vp, C.c_size_t, vp, C.c_size_t, C.c_size_t, C.c_size_t]),
         "fhe_frac_encode": (i32, [u32, u64, C.c_double, u32, u32, u32, u64p]),
         "fhe_add": (i32, [vp, vp, vp, u64, u32]),
         "fhe_sub": (i32, [vp, vp, vp, u64, u32]),
@@ -124,7 +125,7 @@ def lib():
 EXPORTED_SYMBOLS = (
     "fhe_last_error", "fhe_version", "fhe_ctx_create", "fhe_ctx_destroy", "fhe_ctx_sync",
     "fhe_default_coeff_modulus", "fhe_ct_bytes", "fhe_device_alloc", "fhe_device_free", "fhe_host_alloc",
-    "fhe_host_free", "fhe_upload", "fhe_download", "fhe_device_copy", "fhe_frac_encode", "fhe_add", "fhe_sub", "fhe_negate",
+    "fhe_host_free", "fhe_upload", "fhe_download", "fhe_device_copy", "fhe_device_copy_2d", "fhe_frac_encode", "fhe_add", "fhe_sub", "fhe_negate",
     "fhe_ptab_create", "fhe_ptab_destroy", "fhe_multiply_plain", "fhe_add_plain", "fhe_sub_plain",
     "fhe_ntt_forward", "fhe_ntt_inverse", "fhe_dct_plan_create", "fhe_dct_plan_destroy",
     "fhe_dct8x8_quantize", "fhe_dct8x8_quantize_host", "fhe_fill_uniform", "fhe_checksum",

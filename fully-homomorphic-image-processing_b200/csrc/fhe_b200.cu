@@ -453,6 +453,13 @@ int fhe_ctx_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, int de
     CU_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10) return fail(FHE_ERR_CUDA, "libfhe_b200 is built for sm_100a only");
     c->sm_count = prop.multiProcessorCount;
+    {
+        // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     if (cuda_stream) c->stream = (cudaStream_t)cuda_stream;
     else {
         CU_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -549,14 +556,18 @@ int fhe_device_alloc(fhe_ctx *c, size_t bytes, void **dptr)
 {
     if (int rc = check_ctx(c)) return rc;
     if (!dptr) return fail(FHE_ERR_INVALID_ARGUMENT, "null output");
-    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
-    if (e != cudaSuccess) return fail(FHE_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    // stream-ordered allocation from the device's pool (kept cached, see fhe_ctx_create): the
+    // seal-shaped host layer creates and drops a temporary ciphertext per Evaluator call, and a
+    // cudaMalloc / cudaFree pair would synchronise the device every time
+    cudaError_t e = cudaMallocAsync(dptr, bytes ? bytes : 1, c->stream);
+    if (e != cudaSuccess) return fail(FHE_ERR_ALLOC, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
     return FHE_OK;
 }
 int fhe_device_free(fhe_ctx *c, void *dptr)
 {
     if (int rc = check_ctx(c)) return rc;
-    CU_TRY(cudaFree(dptr));
+    if (!dptr) return FHE_OK;
+    CU_TRY(cudaFreeAsync(dptr, c->stream));
     return FHE_OK;
 }
 int fhe_host_alloc(size_t bytes, void **hptr)
@@ -591,6 +602,14 @@ int fhe_device_copy(fhe_ctx *c, void *dst, const void *src, size_t bytes)
     if (int rc = check_ctx(c)) return rc;
     if (!dst || !src) return fail(FHE_ERR_INVALID_ARGUMENT, "null buffer");
     CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    return FHE_OK;
+}
+int fhe_device_copy_2d(fhe_ctx *c, void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t width, size_t rows)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!dst || !src || width > dst_pitch || width > src_pitch) return fail(FHE_ERR_INVALID_ARGUMENT, "bad 2-D copy");
+    if (!rows || !width) return FHE_OK;
+    CU_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width, rows, cudaMemcpyDeviceToDevice, c->stream));
     return FHE_OK;
 }
 

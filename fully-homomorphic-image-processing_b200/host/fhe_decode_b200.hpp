@@ -23,20 +23,27 @@
 namespace seal_b200 {
 
 namespace detail {
-// shared body: the two series differ only in the sign of every coefficient
-inline void taylor_3pi2(Ciphertext &x, Ciphertext &res, double sign, Evaluator &evaluator, FractionalEncoder &encoder,
+inline void fresh_encrypt(Encryptor &e, const Plaintext &p, Ciphertext &res, const Ciphertext &) { e.encrypt(p, res); }
+inline void fresh_encrypt(Encryptor &e, const Plaintext &p, CiphertextBatch &res, const CiphertextBatch &like)
+{
+    e.encrypt(p, res, like.count());
+}
+// shared body: the two series differ only in the sign of every coefficient.  CT = Ciphertext (the
+// reference's call) or CiphertextBatch (the same graph on many independent arguments at once).
+template <class CT>
+inline void taylor_3pi2(CT &x, CT &res, double sign, Evaluator &evaluator, FractionalEncoder &encoder,
                         Encryptor &encryptor)
 {
-    encryptor.encrypt(encoder.encode(0.0), res);
+    fresh_encrypt(encryptor, encoder.encode(0.0), res, x);
 
-    Ciphertext shifted_x(x);
+    CT shifted_x(x);
     evaluator.add_plain(shifted_x, encoder.encode(-3 * M_PI / 2.0));
 
-    Ciphertext power2(shifted_x);
-    Ciphertext power4(shifted_x);
-    Ciphertext power6(shifted_x);
-    Ciphertext power8(shifted_x);
-    Ciphertext power10(shifted_x);
+    CT power2(shifted_x);
+    CT power4(shifted_x);
+    CT power6(shifted_x);
+    CT power8(shifted_x);
+    CT power10(shifted_x);
 
     // 2nd order term
     evaluator.square(power2);
@@ -85,31 +92,45 @@ inline void homomorphic_cos(Ciphertext &x, Ciphertext &res, Evaluator &evaluator
     detail::taylor_3pi2(x, res, -1.0, evaluator, encoder, encryptor);
 }
 
-inline void approximated_step(Ciphertext &amplitude, Ciphertext &index, Ciphertext &count, int order, int degree,
-                              double delta, int width, int height, std::vector<Ciphertext> &run, Evaluator &evaluator,
+inline void homomorphic_sin(CiphertextBatch &x, CiphertextBatch &res, Evaluator &evaluator, FractionalEncoder &encoder,
+                            Encryptor &encryptor)
+{
+    detail::taylor_3pi2(x, res, 1.0, evaluator, encoder, encryptor);
+}
+inline void homomorphic_cos(CiphertextBatch &x, CiphertextBatch &res, Evaluator &evaluator, FractionalEncoder &encoder,
+                            Encryptor &encryptor)
+{
+    detail::taylor_3pi2(x, res, -1.0, evaluator, encoder, encryptor);
+}
+
+// CT = Ciphertext: the reference's call (one run-length pair).  CT = CiphertextBatch: the same graph
+// on `count()` independent (amplitude, index, count) triples at once.
+template <class CT>
+inline void approximated_step(CT &amplitude, CT &index, CT &count, int order, int degree,
+                              double delta, int width, int height, std::vector<CT> &run, Evaluator &evaluator,
                               FractionalEncoder &encoder, Encryptor &encryptor)
 {
-    Ciphertext b(count);
+    CT b(count);
     evaluator.multiply_plain(b, encoder.encode(0.5));
-    Ciphertext offset(index);
+    CT offset(index);
     evaluator.add(offset, b);
     evaluator.add_plain(offset, encoder.encode(-0.5));
     evaluator.negate(offset);
     evaluator.add_plain(b, encoder.encode(delta - 0.5));
     for (int i = 0; i < width * height; i++) {
-        Ciphertext c(b);
+        CT c(b);
         evaluator.multiply_plain(c, encoder.encode(1.0 / ((double)order)));
         for (int j = 1; j <= degree; j++) {
             double arg_factor = ((float)j) * M_PI / ((double)order);
-            Ciphertext sin_arg(b);
+            CT sin_arg(b);
             evaluator.multiply_plain(sin_arg, encoder.encode(arg_factor));
-            Ciphertext cos_arg(offset);
+            CT cos_arg(offset);
             evaluator.add_plain(offset, encoder.encode(i));
             evaluator.multiply_plain(cos_arg, encoder.encode(arg_factor));
-            Ciphertext sin_factor, cos_factor;
+            CT sin_factor, cos_factor;
             homomorphic_sin(sin_arg, sin_factor, evaluator, encoder, encryptor);
             homomorphic_cos(cos_arg, cos_factor, evaluator, encoder, encryptor);
-            Ciphertext term(sin_factor);
+            CT term(sin_factor);
             evaluator.multiply(term, cos_factor);
             evaluator.multiply_plain(term, encoder.encode(2.0 / (M_PI * ((float)j))));
             evaluator.add(c, term);

@@ -35,39 +35,40 @@ namespace seal_b200 {
 constexpr int BILINEAR = 0;  // fhe_resize.h:14
 constexpr int BICUBIC = 1;   // fhe_resize.h:15
 
-inline void Cubic(Ciphertext &result, Ciphertext &A, Ciphertext &B, Ciphertext &C, Ciphertext &D, Ciphertext &t,
-                  Evaluator &evaluator, FractionalEncoder &encoder, Encryptor &encryptor)
+namespace detail {
+// The bodies of Cubic and Linear, written once for any ciphertext type the Evaluator overloads
+// (one seal-style Ciphertext, or a CiphertextBatch = the same graph on a whole row of pixels).
+template <class CT>
+inline void cubic_body(CT &result, CT &A, CT &B, CT &C, CT &D, CT &t, Evaluator &evaluator, FractionalEncoder &encoder)
 {
-    (void)encryptor;
-    auto start = std::chrono::steady_clock::now();
-    Ciphertext a, b, c, d;
-    Ciphertext boaz1(A);
-    Ciphertext boaz2(B); evaluator.multiply_plain(boaz2, encoder.encode(3));
+    CT a, b, c, d;
+    CT boaz1(A);
+    CT boaz2(B); evaluator.multiply_plain(boaz2, encoder.encode(3));
     evaluator.sub(boaz2, boaz1);
-    Ciphertext boaz3(C); evaluator.multiply_plain(boaz3, encoder.encode(3));
+    CT boaz3(C); evaluator.multiply_plain(boaz3, encoder.encode(3));
     evaluator.sub(boaz2, boaz3);
-    Ciphertext boaz4(D);
+    CT boaz4(D);
     evaluator.add(boaz2, boaz4);
     a = boaz2;
 
-    Ciphertext boaz5(A); evaluator.multiply_plain(boaz5, encoder.encode(2));
-    Ciphertext boaz6(B); evaluator.multiply_plain(boaz6, encoder.encode(5));
+    CT boaz5(A); evaluator.multiply_plain(boaz5, encoder.encode(2));
+    CT boaz6(B); evaluator.multiply_plain(boaz6, encoder.encode(5));
     evaluator.sub(boaz5, boaz6);
-    Ciphertext boaz7(C); evaluator.multiply_plain(boaz7, encoder.encode(4));
+    CT boaz7(C); evaluator.multiply_plain(boaz7, encoder.encode(4));
     evaluator.add(boaz5, boaz7);
-    Ciphertext boaz8(D);
+    CT boaz8(D);
     evaluator.sub(boaz5, boaz8);
     b = boaz5;
 
-    Ciphertext boaz9(A);
-    Ciphertext boaz10(C);
+    CT boaz9(A);
+    CT boaz10(C);
     evaluator.sub(boaz10, boaz9);
     c = boaz10;
 
     d = B;
 
-    Ciphertext t2(t); evaluator.square(t2);
-    Ciphertext t3(t); evaluator.multiply(t3, t);  // sic: t*t (fhe_resize.h:175)
+    CT t2(t); evaluator.square(t2);
+    CT t3(t); evaluator.multiply(t3, t);  // sic: t*t (fhe_resize.h:175)
 
     evaluator.multiply(a, t3);
     evaluator.multiply(b, t2);
@@ -78,24 +79,53 @@ inline void Cubic(Ciphertext &result, Ciphertext &A, Ciphertext &B, Ciphertext &
     evaluator.multiply_plain(a, encoder.encode(0.5));
     evaluator.add(a, d);
     result = a;
-    evaluator.context().sync();
-    auto diff = std::chrono::steady_clock::now() - start;
-    std::cout << std::chrono::duration<double, std::milli>(diff).count() << ',';
 }
+template <class CT>
+inline void linear_body(CT &result, CT &A, CT &B, CT &t, Evaluator &evaluator, FractionalEncoder &encoder)
+{
+    CT boaz1(t); evaluator.negate(boaz1); evaluator.add_plain(boaz1, encoder.encode(1.0));
+    evaluator.multiply(boaz1, A);
+    CT boaz2(B); evaluator.multiply(boaz2, t);
+    evaluator.add(boaz1, boaz2);
+    result = boaz1;
+}
+struct CsvMs {  // the reference prints the wall time of each call in ms followed by ','
+    const Context &ctx;
+    std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
+    explicit CsvMs(const Context &c) : ctx(c) {}
+    ~CsvMs()
+    {
+        fhe_ctx_sync(ctx.handle());
+        auto diff = std::chrono::steady_clock::now() - start;
+        std::cout << std::chrono::duration<double, std::milli>(diff).count() << ',';
+    }
+};
+}  // namespace detail
 
+inline void Cubic(Ciphertext &result, Ciphertext &A, Ciphertext &B, Ciphertext &C, Ciphertext &D, Ciphertext &t,
+                  Evaluator &evaluator, FractionalEncoder &encoder, Encryptor &encryptor)
+{
+    (void)encryptor;
+    detail::CsvMs timer(evaluator.context());
+    detail::cubic_body(result, A, B, C, D, t, evaluator, encoder);
+}
 inline void Linear(Ciphertext &result, Ciphertext &A, Ciphertext &B, Ciphertext &t, Evaluator &evaluator,
                    FractionalEncoder &encoder, Encryptor &encryptor)
 {
     (void)encryptor;
-    auto start = std::chrono::steady_clock::now();
-    Ciphertext boaz1(t); evaluator.negate(boaz1); evaluator.add_plain(boaz1, encoder.encode(1.0));
-    evaluator.multiply(boaz1, A);
-    Ciphertext boaz2(B); evaluator.multiply(boaz2, t);
-    evaluator.add(boaz1, boaz2);
-    result = boaz1;
-    evaluator.context().sync();
-    auto diff = std::chrono::steady_clock::now() - start;
-    std::cout << std::chrono::duration<double, std::milli>(diff).count() << ',';
+    detail::CsvMs timer(evaluator.context());
+    detail::linear_body(result, A, B, t, evaluator, encoder);
+}
+// the same graphs on `count` independent inputs at once (no timing output: not a reference call)
+inline void Cubic(CiphertextBatch &result, CiphertextBatch &A, CiphertextBatch &B, CiphertextBatch &C, CiphertextBatch &D,
+                  CiphertextBatch &t, Evaluator &evaluator, FractionalEncoder &encoder)
+{
+    detail::cubic_body(result, A, B, C, D, t, evaluator, encoder);
+}
+inline void Linear(CiphertextBatch &result, CiphertextBatch &A, CiphertextBatch &B, CiphertextBatch &t, Evaluator &evaluator,
+                   FractionalEncoder &encoder)
+{
+    detail::linear_body(result, A, B, t, evaluator, encoder);
 }
 
 struct SImageData {
@@ -240,6 +270,99 @@ inline void ResizeImage(const std::string &infile_str, int original_width, int o
 {
     ResizeImage(raw_file_source(evaluator.context(), infile_str), original_width, original_height, destImage, dest_width,
                 dest_height, inter, evaluator, encoder, encryptor);
+}
+
+// ---------------------------------------------------------------------------------------------
+// B200-first variant of ResizeImage + SampleBicubic / SampleLinear: identical arithmetic and
+// identical results (tests/cpp/test_resize_decode.cpp compares them ciphertext by ciphertext), but
+// one output ROW is sampled at a time: the 16 (4) neighbour pixels of every output pixel and
+// channel are gathered into CiphertextBatches of dest_width * 3 elements and each Evaluator call of
+// the Cubic / Linear graph covers the whole row.  The two fractions are encrypted once per output
+// pixel, in the reference's call order (x then y), and shared by the three channels.
+inline void ResizeImageBatched(const CiphertextSource &load, int original_width, int original_height, SImageData &destImage,
+                               int dest_width, int dest_height, int inter, Evaluator &evaluator, FractionalEncoder &encoder,
+                               Encryptor &encryptor)
+{
+    const Context &ctx = evaluator.context();
+    SImageData srcImage;
+    srcImage.width = original_width;
+    srcImage.height = original_height;
+    srcImage.start = 0;
+    const int init_rows = inter == BILINEAR ? 2 : 4, taps = init_rows;
+    if (inter != BILINEAR && inter != BICUBIC) throw std::invalid_argument("unknown interpolation");
+    Ciphertext c;
+    auto load_pixel = [&]() {
+        std::vector<Ciphertext> pixel;
+        for (int j = 0; j < 3; ++j) {
+            load(c);
+            pixel.push_back(c);
+        }
+        return pixel;
+    };
+    for (int i = 0; i < original_width * init_rows; i++) srcImage.pixels.push_back(load_pixel());
+    destImage.width = dest_width;
+    destImage.height = dest_height;
+    destImage.start = 0;
+    destImage.pixels.clear();
+    const size_t count = (size_t)dest_width * 3;
+    for (int y = 0; y < dest_height; ++y) {
+        float v = float(y) / float(dest_height - 1) * float(srcImage.height) - 0.5;
+        int new_start = std::min(int(v) - init_rows / 2 + 1, srcImage.height - init_rows) * srcImage.width;
+        if (new_start > srcImage.start) {
+            for (int i = srcImage.start + init_rows * srcImage.width; i < new_start; i++)
+                for (int j = 0; j < 3; j++) load(c);
+            std::vector<std::vector<Ciphertext>> new_pixels;
+            int present = 0;
+            for (int i = new_start - srcImage.start; i < init_rows * srcImage.width; i++) {
+                new_pixels.push_back(std::move(srcImage.pixels[(size_t)i]));
+                present++;
+            }
+            for (int i = present; i < init_rows * srcImage.width; i++) new_pixels.push_back(load_pixel());
+            srcImage.start = new_start;
+            srcImage.pixels = std::move(new_pixels);
+        }
+        // gather: tap[r][cidx] holds, for every (x, channel), the neighbour (xint + off + cidx, yint + off + r)
+        std::vector<std::vector<CiphertextBatch>> tap((size_t)taps, std::vector<CiphertextBatch>());
+        for (auto &row : tap)
+            for (int cidx = 0; cidx < taps; ++cidx) row.emplace_back(ctx, count, 2);
+        CiphertextBatch xfract(ctx, count, 2), yfract(ctx, count, 2);
+        const int off = inter == BICUBIC ? -1 : 0;
+        const int yint = int(v);
+        for (int x = 0; x < dest_width; ++x) {
+            float u = float(x) / float(dest_width - 1) * float(srcImage.width) - 0.5;
+            const int xint = int(u);
+            Ciphertext xf, yf;
+            encryptor.encrypt(encoder.encode(u - std::floor(u)), xf);
+            encryptor.encrypt(encoder.encode(v - std::floor(v)), yf);
+            for (int ch = 0; ch < 3; ++ch) {
+                xfract.set((size_t)x * 3 + ch, xf);
+                yfract.set((size_t)x * 3 + ch, yf);
+            }
+            for (int r = 0; r < taps; ++r)
+                for (int cidx = 0; cidx < taps; ++cidx) {
+                    int px = std::min(std::max(xint + off + cidx, 0), srcImage.width - 1);
+                    int py = std::min(std::max(yint + off + r, 0), srcImage.height - 1);
+                    const std::vector<Ciphertext> &pixel = srcImage.pixels.at((size_t)(py * srcImage.width + px - srcImage.start));
+                    for (int ch = 0; ch < 3; ++ch) tap[(size_t)r][(size_t)cidx].set((size_t)x * 3 + ch, pixel[(size_t)ch]);
+                }
+        }
+        CiphertextBatch out;
+        if (inter == BICUBIC) {
+            std::vector<CiphertextBatch> col(4);
+            for (int r = 0; r < 4; ++r) Cubic(col[(size_t)r], tap[(size_t)r][0], tap[(size_t)r][1], tap[(size_t)r][2], tap[(size_t)r][3], xfract, evaluator, encoder);
+            Cubic(out, col[0], col[1], col[2], col[3], yfract, evaluator, encoder);
+        } else {
+            CiphertextBatch col0, col1;
+            Linear(col0, tap[0][0], tap[0][1], xfract, evaluator, encoder);
+            Linear(col1, tap[1][0], tap[1][1], xfract, evaluator, encoder);
+            Linear(out, col0, col1, yfract, evaluator, encoder);
+        }
+        for (int x = 0; x < dest_width; ++x) {
+            std::vector<Ciphertext> sample;
+            for (int ch = 0; ch < 3; ++ch) sample.push_back(out.get((size_t)x * 3 + ch));
+            destImage.pixels.push_back(std::move(sample));
+        }
+    }
 }
 
 }  // namespace seal_b200

@@ -224,6 +224,74 @@ inline bool is_contiguous(const std::vector<Ciphertext> &v)
     return true;
 }
 
+// `count` independent ciphertexts of equal size in one allocation, [ct][size][k][n]: the unit the
+// device works on efficiently.  The reference evaluates its graphs one seal::Ciphertext at a time
+// (one output pixel, one 4x4 neighbourhood); the graphs in fhe_resize_b200.hpp / fhe_decode_b200.hpp
+// are templates that run unchanged on a Ciphertext or on a CiphertextBatch -- every Evaluator call
+// then covers the whole batch (a row of output pixels) with the same launches.
+class CiphertextBatch {
+public:
+    CiphertextBatch() = default;
+    CiphertextBatch(const Context &ctx, size_t count, uint32_t size = 2) : ctx_(&ctx), count_(count), size_(size)
+    {
+        arena_ = std::make_shared<Arena>(ctx, ctx.ct_words(size) * count);
+    }
+    CiphertextBatch(const CiphertextBatch &o) : ctx_(o.ctx_), count_(o.count_), size_(o.size_)
+    {
+        if (!o.arena_) return;
+        arena_ = std::make_shared<Arena>(*ctx_, o.arena_->words());
+        check(fhe_device_copy(ctx_->handle(), arena_->data(), o.arena_->data(), o.arena_->words() * sizeof(uint64_t)));
+    }
+    CiphertextBatch(CiphertextBatch &&) noexcept = default;
+    CiphertextBatch &operator=(const CiphertextBatch &o)
+    {
+        if (this != &o) {
+            CiphertextBatch t(o);
+            *this = std::move(t);
+        }
+        return *this;
+    }
+    CiphertextBatch &operator=(CiphertextBatch &&) noexcept = default;
+
+    size_t count() const { return count_; }
+    uint32_t size() const { return size_; }
+    bool valid() const { return arena_ != nullptr; }
+    const Context *context() const { return ctx_; }
+    uint64_t *device_data() const { return arena_ ? arena_->data() : nullptr; }
+    uint64_t *element(size_t i) const { return arena_->data() + i * ctx_->ct_words(size_); }
+    // element i <- c (device copy); sizes must agree
+    void set(size_t i, const Ciphertext &c)
+    {
+        if (i >= count_ || !c.valid() || c.size() != size_ || c.context() != ctx_) throw std::invalid_argument("batch element mismatch");
+        check(fhe_device_copy(ctx_->handle(), element(i), c.device_data(), ctx_->ct_words(size_) * sizeof(uint64_t)));
+    }
+    Ciphertext get(size_t i) const
+    {
+        if (i >= count_) throw std::invalid_argument("batch index out of range");
+        Ciphertext c(*ctx_, size_);
+        check(fhe_device_copy(ctx_->handle(), c.device_data(), element(i), ctx_->ct_words(size_) * sizeof(uint64_t)));
+        return c;
+    }
+    // the same ciphertexts in storage for `new_size` >= size() polynomials, missing ones zero
+    CiphertextBatch widened(uint32_t new_size) const
+    {
+        if (new_size < size_) throw std::invalid_argument("cannot shrink a ciphertext");
+        CiphertextBatch r(*ctx_, count_, new_size);
+        const size_t wo = ctx_->ct_words(size_) * sizeof(uint64_t), wn = ctx_->ct_words(new_size) * sizeof(uint64_t);
+        check(fhe_device_zero(ctx_->handle(), r.device_data(), wn * count_));
+        check(fhe_device_copy_2d(ctx_->handle(), r.device_data(), wn, device_data(), wo, wo, count_));
+        return r;
+    }
+    void upload(const uint64_t *host) { check(fhe_upload(ctx_->handle(), device_data(), host, arena_->words() * 8)); }
+    void download(uint64_t *host) const { check(fhe_download(ctx_->handle(), host, device_data(), arena_->words() * 8)); }
+
+private:
+    const Context *ctx_ = nullptr;
+    std::shared_ptr<Arena> arena_;
+    size_t count_ = 0;
+    uint32_t size_ = 0;
+};
+
 // seal::Encryptor.  fhe_image.h only passes it through; fhe_resize.h (:230-266) and fhe_decode.h
 // (:54,134) encrypt PUBLIC scalars on the server with it.  Two server-side forms:
 //   * Encryptor(fn): a callback that produces the ciphertext (a real public-key encryption made by
@@ -238,6 +306,17 @@ public:
     explicit Encryptor(Fn fn) : fn_(std::move(fn)) {}
     explicit Encryptor(const Context &ctx) : ctx_(&ctx) {}
     void encrypt(const Plaintext &plain, Ciphertext &destination) const;
+    // `count` fresh encryptions of the same plaintext (one callback invocation each)
+    void encrypt(const Plaintext &plain, CiphertextBatch &destination, size_t count) const
+    {
+        if (!fn_ && !ctx_) throw std::logic_error("this Encryptor holds no public key and no context");
+        Ciphertext c;
+        for (size_t i = 0; i < count; ++i) {
+            if (fn_ || i == 0) encrypt(plain, c);
+            if (i == 0) destination = CiphertextBatch(*c.context(), count, c.size());
+            destination.set(i, c);
+        }
+    }
 
 private:
     Fn fn_;
@@ -327,6 +406,54 @@ public:
         check(fhe_relinearize(ctx_->handle(), a.device_data(), a.size(), evk.handle(), dest.device_data(), 1));
         a = std::move(dest);
     }
+    // ---- the same operations on a CiphertextBatch: one call, `count` independent ciphertexts ----
+    void add(CiphertextBatch &a, const CiphertextBatch &b) { binary_batch(a, b, fhe_add); }
+    void sub(CiphertextBatch &a, const CiphertextBatch &b) { binary_batch(a, b, fhe_sub); }
+    void negate(CiphertextBatch &a)
+    {
+        require(a);
+        check(fhe_negate(ctx_->handle(), a.device_data(), a.count(), a.size()));
+    }
+    void multiply_plain(CiphertextBatch &a, const Plaintext &p)
+    {
+        require(a);
+        if (p.is_zero()) throw std::invalid_argument("plain cannot be zero");
+        check(fhe_multiply_plain(ctx_->handle(), a.device_data(), a.count(), a.size(), table(p), 0));
+    }
+    void add_plain(CiphertextBatch &a, const Plaintext &p)
+    {
+        require(a);
+        check(fhe_add_plain(ctx_->handle(), a.device_data(), a.count(), a.size(), table(p), 0));
+    }
+    void sub_plain(CiphertextBatch &a, const Plaintext &p)
+    {
+        require(a);
+        check(fhe_sub_plain(ctx_->handle(), a.device_data(), a.count(), a.size(), table(p), 0));
+    }
+    void multiply(CiphertextBatch &a, const CiphertextBatch &b)
+    {
+        require(a);
+        require(b);
+        if (a.count() != b.count()) throw std::invalid_argument("batch counts differ");
+        CiphertextBatch dest(*ctx_, a.count(), a.size() + b.size() - 1);
+        check(fhe_multiply(ctx_->handle(), a.device_data(), a.size(), b.device_data(), b.size(), dest.device_data(), a.count()));
+        a = std::move(dest);
+    }
+    void square(CiphertextBatch &a)
+    {
+        require(a);
+        CiphertextBatch dest(*ctx_, a.count(), 2 * a.size() - 1);
+        check(fhe_square(ctx_->handle(), a.device_data(), a.size(), dest.device_data(), a.count()));
+        a = std::move(dest);
+    }
+    void relinearize(CiphertextBatch &a, const EvaluationKeys &evk)
+    {
+        require(a);
+        if (a.size() <= 2) return;
+        CiphertextBatch dest(*ctx_, a.count(), 2);
+        check(fhe_relinearize(ctx_->handle(), a.device_data(), a.size(), evk.handle(), dest.device_data(), a.count()));
+        a = std::move(dest);
+    }
     const Context &context() const { return *ctx_; }
     // per-evaluator cache slot for the fused-graph plans of fhe_image_b200.hpp
     std::shared_ptr<void> &plan_slot(const std::string &key) { return plans_[key]; }
@@ -335,6 +462,26 @@ private:
     void require(const Ciphertext &a) const
     {
         if (!a.valid() || a.context() != ctx_) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    }
+    void require(const CiphertextBatch &a) const
+    {
+        if (!a.valid() || a.context() != ctx_) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+    }
+    // unequal sizes: the smaller operand is re-strided into zero-padded storage of the larger size,
+    // then the equal-size kernel runs (exactly SEAL's "missing polynomials are zero")
+    template <class F>
+    void binary_batch(CiphertextBatch &a, const CiphertextBatch &b, F fn)
+    {
+        require(a);
+        require(b);
+        if (a.count() != b.count()) throw std::invalid_argument("batch counts differ");
+        if (a.size() < b.size()) a = a.widened(b.size());
+        if (b.size() < a.size()) {
+            const CiphertextBatch bw = b.widened(a.size());
+            check(fn(ctx_->handle(), a.device_data(), bw.device_data(), a.count(), a.size()));
+            return;  // bw is released in stream order (fhe_device_free)
+        }
+        check(fn(ctx_->handle(), a.device_data(), b.device_data(), a.count(), a.size()));
     }
     template <class F>
     void binary(Ciphertext &a, const Ciphertext &b, F fn)

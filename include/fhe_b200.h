@@ -72,6 +72,11 @@ int fhe_download(fhe_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes
 /* device -> device on the context's stream: seal::Ciphertext copy construction / assignment
  * (`Ciphertext boaz1(data[0])`, fhe_image.h:207). */
 int fhe_device_copy(fhe_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
+/* `rows` runs of `width` bytes, `*_pitch` bytes apart (device -> device, on the stream): gathers
+ * ciphertexts into a batch, or re-strides a batch of size-s ciphertexts into size-s' storage (what
+ * Evaluator::add does when the sizes differ). */
+int fhe_device_copy_2d(fhe_ctx *ctx, void *dst_dev, size_t dst_pitch, const void *src_dev, size_t src_pitch,
+                       size_t width, size_t rows);
 
 /* ---- encoder (host logic) -----------------------------------------------------------------
  * seal::FractionalEncoder(plain_modulus, poly_modulus, int_coeffs, frac_coeffs, base).encode,

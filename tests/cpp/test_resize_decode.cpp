@@ -113,6 +113,44 @@ int main(int argc, char **argv)
                 dump(ch);
             }
 
+        // the row-batched sampler (one Evaluator call per graph op for a whole output row) gives the
+        // same ciphertexts as the reference-style per-pixel sampler, bicubic and bilinear
+        auto same = [&](const Ciphertext &x, const Ciphertext &y) {
+            if (x.size() != y.size()) return false;
+            std::vector<uint64_t> hx(ctx.ct_words(x.size())), hy(hx.size());
+            x.download(hx.data());
+            y.download(hy.data());
+            return hx == hy;
+        };
+        for (int inter : {BICUBIC, BILINEAR}) {
+            size_t src1 = 34, src2 = 34, f1 = 16, f2 = 16;
+            Encryptor fr1([&](const Plaintext &, Ciphertext &dst) { dst = ct_at(f1++); });
+            Encryptor fr2([&](const Plaintext &, Ciphertext &dst) { dst = ct_at(f2++); });
+            SImageData d1, d2;
+            ResizeImage([&](Ciphertext &dst) { dst = ct_at(src1++); }, 5, 6, d1, 3, 3, inter, evaluator, encoder, fr1);
+            ResizeImageBatched([&](Ciphertext &dst) { dst = ct_at(src2++); }, 5, 6, d2, 3, 3, inter, evaluator, encoder, fr2);
+            REQUIRE(d1.pixels.size() == 9 && d2.pixels.size() == 9 && f1 == f2 && src1 == src2);
+            for (size_t i = 0; i < 9; ++i)
+                for (size_t ch = 0; ch < 3; ++ch) {
+                    REQUIRE(d1.pixels[i][ch].size() == (inter == BICUBIC ? 6u : 4u));
+                    REQUIRE(same(d1.pixels[i][ch], d2.pixels[i][ch]));
+                }
+        }
+        // batched sine == per-ciphertext sine
+        {
+            CiphertextBatch xs(ctx, 3, 2), rs;
+            for (size_t i = 0; i < 3; ++i) xs.set(i, ct_at(i));
+            next_zero = 8;
+            homomorphic_sin(xs, rs, evaluator, encoder, zeros);
+            REQUIRE(rs.count() == 3 && rs.size() == 11 && next_zero == 11);
+            for (size_t i = 0; i < 3; ++i) {
+                Ciphertext xi = ct_at(i), ri;
+                next_zero = 8 + i;
+                homomorphic_sin(xi, ri, evaluator, encoder, zeros);
+                REQUIRE(same(ri, rs.get(i)));
+            }
+        }
+
         // the key-less deterministic Encryptor: (Delta*m, 0) decrypts to m and is accepted by the graphs
         Encryptor transparent(ctx);
         Ciphertext tz;

@@ -1,0 +1,61 @@
+// bench_resize.cpp -- BASELINE.json config 3 (server_resize bicubic, FractionalEncoder, n=8192) on
+// one B200, through the C++ host layer: ResizeImageBatched (host/fhe_resize_b200.hpp) on synthetic
+// uniform ciphertexts with the key-less transparent Encryptor for the public fractions.
+// The geometry is scaled down (default 128x16 -> 64x8, 2:1 like 512x512 -> 256x256); the cost per
+// output pixel does not depend on the image size, so pixels/s extrapolates to the full config.
+// Not the headline bench (bench.py).  Usage: bench_resize [n] [ow] [oh]   -> one JSON line
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <sstream>
+
+#include "../fully-homomorphic-image-processing_b200/host/fhe_resize_b200.hpp"
+
+using namespace seal_b200;
+
+int main(int argc, char **argv)
+{
+    try {
+        const uint32_t n = argc > 1 ? (uint32_t)std::atoi(argv[1]) : 8192;
+        const int ow = argc > 2 ? std::atoi(argv[2]) : 128, oh = argc > 3 ? std::atoi(argv[3]) : 16;
+        const int dw = ow / 2, dh = oh / 2;
+        Context ctx(n);
+        Evaluator evaluator(ctx);
+        FractionalEncoder encoder(ctx, 100, 100);
+        Encryptor encryptor(ctx);  // transparent encryption of the public fractions
+        uint64_t next = 0;
+        CiphertextSource source = [&](Ciphertext &dst) {
+            Ciphertext c(ctx, 2);
+            check(fhe_fill_uniform(ctx.handle(), c.device_data(), next++, 1, 2, 0xC0F3));
+            dst = std::move(c);
+        };
+        struct Quiet {
+            std::ostringstream sink;
+            std::streambuf *old;
+            Quiet() : old(std::cout.rdbuf(sink.rdbuf())) {}
+            ~Quiet() { std::cout.rdbuf(old); }
+        } quiet;
+        for (int inter : {BICUBIC, BILINEAR}) {
+            next = 0;
+            SImageData dest;
+            const uint64_t l0 = fhe_launch_count(ctx.handle());
+            ctx.sync();
+            auto t0 = std::chrono::steady_clock::now();
+            ResizeImageBatched(source, ow, oh, dest, dw, dh, inter, evaluator, encoder, encryptor);
+            ctx.sync();
+            const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const double px = (double)dw * dh;
+            std::printf("{\"what\": \"ResizeImageBatched %s, FractionalEncoder(100,100), n=%u k=%u, %dx%d -> %dx%d RGB, "
+                        "synthetic ciphertexts, transparent fractions\", \"seconds\": %.4f, \"output_pixels_per_s\": %.2f, "
+                        "\"%s_calls_per_s\": %.1f, \"out_ct_size\": %u, \"kernel_launches\": %llu, "
+                        "\"full_config3_512x512_to_256x256_estimate_s\": %.1f}\n",
+                        inter == BICUBIC ? "bicubic" : "bilinear", n, ctx.coeff_mod_count(), ow, oh, dw, dh, s, px / s,
+                        inter == BICUBIC ? "Cubic" : "Linear", (inter == BICUBIC ? 15.0 : 9.0) * px / s,
+                        dest.pixels[0][0].size(), (unsigned long long)(fhe_launch_count(ctx.handle()) - l0), 65536.0 / (px / s));
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "exception: %s\n", e.what());
+        return 1;
+    }
+}
