@@ -1,0 +1,101 @@
+// seal_wire_b200.hpp -- seal::Ciphertext::save / load wire format (SEAL 2.3), SURVEY.md 8f-N2.
+//
+// The reference's client and server exchange ciphertexts as files of concatenated
+// seal::Ciphertext::save records with no framing (client_jpeg.cpp:140-165 writes, server_jpeg.cpp:117
+// reads, :146-153 writes back).  SEAL is absent from /root/reference, so the layout below is the
+// published 2.3 layout as recalled in SURVEY.md Appendix A.8 -- UNVERIFIED against real SEAL files:
+//
+//   hash block     4 x uint64   (SHA-3 of the encryption parameters in SEAL; opaque here)
+//   size_capacity  int32
+//   size           int32        number of polynomials
+//   poly_coeff_count int32      n + 1  (SEAL 2.3 keeps a zero top coefficient per limb)
+//   coeff_mod_count  int32      k
+//   data           size * k * (n + 1) uint64, [poly][limb][coeff], little endian
+//
+// The device layout drops the padding coefficient ([poly][limb][n]); these helpers convert.  The
+// hash block cannot be recomputed without SEAL's hash; save() writes the block given by the caller
+// (by default the one seen on the last load, so a server echoes its client's block) and load() can
+// check it against an expected value.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <istream>
+#include <ostream>
+#include <stdexcept>
+#include <vector>
+
+#include "seal_b200.hpp"
+
+namespace seal_b200 {
+
+using hash_block_type = std::array<uint64_t, 4>;
+
+struct WireHeader {
+    hash_block_type hash{};
+    int32_t size_capacity = 0, size = 0, poly_coeff_count = 0, coeff_mod_count = 0;
+};
+
+// Reads one record; `host` receives size * k * n words in device layout.  Returns false at a clean
+// end of stream (no bytes left), throws std::invalid_argument on a truncated or mismatching record.
+inline bool load_ciphertext(std::istream &in, const Context &ctx, std::vector<uint64_t> &host, WireHeader &hdr)
+{
+    in.read((char *)hdr.hash.data(), sizeof(uint64_t) * 4);
+    if (in.gcount() == 0 && in.eof()) return false;
+    int32_t meta[4];
+    in.read((char *)meta, sizeof(meta));
+    if (!in) throw std::invalid_argument("ciphertext stream: truncated header");
+    hdr.size_capacity = meta[0];
+    hdr.size = meta[1];
+    hdr.poly_coeff_count = meta[2];
+    hdr.coeff_mod_count = meta[3];
+    const uint32_t n = ctx.poly_degree(), k = ctx.coeff_mod_count();
+    if (hdr.size < 2 || hdr.size > hdr.size_capacity || hdr.poly_coeff_count != (int32_t)n + 1 || hdr.coeff_mod_count != (int32_t)k)
+        throw std::invalid_argument("ciphertext is not valid for encryption parameters");
+    host.resize((size_t)hdr.size * k * n);
+    std::vector<uint64_t> row(n + 1);
+    for (size_t p = 0; p < (size_t)hdr.size * k; ++p) {
+        in.read((char *)row.data(), (std::streamsize)(row.size() * sizeof(uint64_t)));
+        if (!in) throw std::invalid_argument("ciphertext stream: truncated data");
+        if (row[n] != 0) throw std::invalid_argument("ciphertext stream: non-zero padding coefficient");
+        for (uint32_t i = 0; i < n; ++i)
+            if (row[i] >= ctx.coeff_modulus()[p % k]) throw std::invalid_argument("ciphertext coefficient is not reduced");
+        std::copy(row.begin(), row.begin() + n, host.begin() + p * n);
+    }
+    // SEAL also stores the (unused) capacity tail
+    const size_t tail = (size_t)(hdr.size_capacity - hdr.size) * k * (n + 1) * sizeof(uint64_t);
+    if (tail) in.ignore((std::streamsize)tail);
+    return true;
+}
+
+inline void save_ciphertext(std::ostream &out, const Context &ctx, const uint64_t *host, uint32_t size, const hash_block_type &hash)
+{
+    const uint32_t n = ctx.poly_degree(), k = ctx.coeff_mod_count();
+    out.write((const char *)hash.data(), sizeof(uint64_t) * 4);
+    const int32_t meta[4] = {(int32_t)size, (int32_t)size, (int32_t)n + 1, (int32_t)k};
+    out.write((const char *)meta, sizeof(meta));
+    const uint64_t zero = 0;
+    for (size_t p = 0; p < (size_t)size * k; ++p) {
+        out.write((const char *)(host + p * n), (std::streamsize)(n * sizeof(uint64_t)));
+        out.write((const char *)&zero, sizeof(zero));
+    }
+    if (!out) throw std::runtime_error("ciphertext stream: write failed");
+}
+
+// Ciphertext-level convenience (one H2D / D2H per record)
+inline bool load_ciphertext(std::istream &in, const Context &ctx, Ciphertext &dst, WireHeader &hdr)
+{
+    std::vector<uint64_t> host;
+    if (!load_ciphertext(in, ctx, host, hdr)) return false;
+    Ciphertext c(ctx, (uint32_t)hdr.size);
+    c.upload(host.data());
+    dst = std::move(c);
+    return true;
+}
+inline void save_ciphertext(std::ostream &out, const Ciphertext &c, const hash_block_type &hash)
+{
+    std::vector<uint64_t> host(c.context()->ct_words(c.size()));
+    c.download(host.data());
+    save_ciphertext(out, *c.context(), host.data(), c.size(), hash);
+}
+
+}  // namespace seal_b200

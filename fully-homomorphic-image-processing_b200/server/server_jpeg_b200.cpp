@@ -1,0 +1,162 @@
+// server_jpeg_b200.cpp -- the reference's homo/server_jpeg.cpp re-hosted on libfhe_b200
+// (SURVEY.md 8f-N3).  Same place in the client/server split, same files and flags:
+//
+//   ./keys/params.txt            "W H C pmod" written by client_jpeg --send (client_jpeg.cpp:88-94)
+//   --file / -f   (default ./image/nothingpersonnel.txt)   per 8x8 tile: R64, G64, B64 ciphertexts
+//   --outfile / -o (default ./image/zoop.txt)               per tile: Y64, Cb64, Cr64 (:146-153)
+//   --ncoeff --fcoeff --cmod --pmod --base                  as server_jpeg.cpp:44-52 (--base is parsed
+//                                                           and, like there (:66), has no effect: base 2)
+//   stdout: "RGBYCC,<64 ms values>,\nDCT,<3 ms values>,\n" per tile (server_jpeg.cpp:126-137) -- the CSV
+//   benchmark/analyze.py parses.  The values are the fused kernels' device times split evenly over
+//   the calls they replace (the colour conversion is the epilogue of the forward transform).
+//
+// Unlike the reference (one tile at a time, one Evaluator call at a time, "three blocks to not get
+// OOM", :109-111) tiles are streamed through the device in chunks: load a chunk from the file,
+// ONE fhe_jpeg_rgb_tiles call (forward NTT + colour conversion, pointwise DCT per channel, inverse
+// NTT), write the chunk back.  The server never loads the secret key (the reference does, "FOR
+// DEBUGGING ONLY", :97-98) and needs no public key on this path.
+// Extra flags: --quantize (also apply quantize_fhe with the JPEG luminance / chrominance tables,
+// fhe_image.h:99-100,294-305 -- the reference's main never calls it), --chunk N (tiles per call).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <string>
+
+#include "../host/fhe_image_b200.hpp"
+#include "../host/seal_wire_b200.hpp"
+
+using namespace seal_b200;
+
+static const double kYQT[64] = {16, 11, 10, 16, 24, 40, 51, 61, 12, 12, 14, 19, 26, 58, 60, 55, 14, 13, 16, 24, 40, 57,
+                                69, 56, 14, 17, 22, 29, 51, 87, 80, 62, 18, 22, 37, 56, 68, 109, 103, 77, 24, 35, 55, 64,
+                                81, 104, 113, 92, 49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+static const double kUVQT[64] = {17, 18, 24, 47, 99, 99, 99, 99, 18, 21, 26, 66, 99, 99, 99, 99, 24, 26, 56, 99, 99, 99,
+                                 99, 99, 47, 66, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99,
+                                 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99, 99};
+static const double kColor[9] = {0.299, 0.587, 0.114, -0.168736, 0.331264, 0.5, 0.5, 0.418688, 0.081312};
+
+static void usage(const char *argv0)
+{
+    std::printf("%s [-f|--file in] [-o|--outfile out] [--ncoeff N] [--fcoeff N] [--cmod n] [--pmod t] [--base b]\n"
+                "        [--quantize] [--chunk tiles] [-v|--verbose] [--help]\n", argv0);
+}
+
+int main(int argc, const char **argv)
+{
+    std::string ctext_infile("./image/nothingpersonnel.txt"), ctext_outfile("./image/zoop.txt");
+    bool verbose = false, quantize = false;
+    int n_number_coeffs = 100, n_fractional_coeffs = 100, n_poly_base = 2;  // fhe_image.h:22-26
+    int plain_modulus = 1 << 14, coeff_modulus = 8192;                       // fhe_image.h:26-27
+    int chunk_tiles = 64;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto val = [&](const char *name) -> std::string {
+            if (i + 1 >= argc) {
+                std::cout << "error parsing options: Option '" << name << "' is missing an argument" << std::endl;
+                std::exit(1);
+            }
+            return argv[++i];
+        };
+        if (a == "-f" || a == "--file") ctext_infile = val("file");
+        else if (a == "-o" || a == "--outfile") ctext_outfile = val("outfile");
+        else if (a == "-v" || a == "--verbose") verbose = true;
+        else if (a == "--ncoeff") n_number_coeffs = std::atoi(val("ncoeff").c_str());
+        else if (a == "--fcoeff") n_fractional_coeffs = std::atoi(val("fcoeff").c_str());
+        else if (a == "--cmod") coeff_modulus = std::atoi(val("cmod").c_str());
+        else if (a == "--pmod") plain_modulus = std::atoi(val("pmod").c_str());
+        else if (a == "--base") n_poly_base = std::atoi(val("base").c_str());
+        else if (a == "--quantize") quantize = true;
+        else if (a == "--chunk") chunk_tiles = std::atoi(val("chunk").c_str());
+        else if (a == "--help") {
+            usage(argv[0]);
+            return 0;
+        } else {
+            std::cout << "error parsing options: Option '" << a << "' does not exist" << std::endl;
+            return 1;
+        }
+    }
+    (void)n_poly_base;  // the reference's override is dead code (server_jpeg.cpp:66): base stays 2
+    if (chunk_tiles < 1) chunk_tiles = 1;
+
+    int WIDTH = 0, HEIGHT = 0, channels = 0;
+    {
+        std::ifstream paramfile("./keys/params.txt");
+        paramfile >> WIDTH >> HEIGHT >> channels;
+        if (!paramfile || channels != 3) {
+            std::fprintf(stderr, "server_jpeg_b200: ./keys/params.txt missing or channels != 3\n");
+            return 1;
+        }
+    }
+    try {
+        Context context((uint32_t)coeff_modulus, (uint64_t)plain_modulus);
+        FractionalEncoder encoder(context, (uint32_t)n_number_coeffs, (uint32_t)n_fractional_coeffs, 2);
+        const uint32_t n = context.poly_degree();
+        auto stack = [&](const double *vals, int count, bool reciprocal) {
+            std::vector<uint64_t> out((size_t)count * n);
+            for (int i = 0; i < count; ++i) {
+                Plaintext p = encoder.encode(reciprocal ? 1 / vals[i] : vals[i]);
+                std::memcpy(out.data() + (size_t)i * n, p.coeffs().data(), n * sizeof(uint64_t));
+            }
+            return out;
+        };
+        const std::vector<uint64_t> color = stack(kColor, 9, false), dct = stack(kDctConstants, 12, false);
+        const std::vector<uint64_t> off = encoder.encode(128.0).coeffs(), eighth = encoder.encode(0.125).coeffs();
+        std::vector<uint64_t> qy, qc;
+        if (quantize) {
+            qy = stack(kYQT, 64, true);
+            qc = stack(kUVQT, 64, true);
+        }
+        fhe_jpeg_plan *plan = nullptr;
+        check(fhe_jpeg_plan_create(context.handle(), color.data(), off.data(), dct.data(), eighth.data(),
+                                   quantize ? qy.data() : nullptr, quantize ? qc.data() : nullptr, &plan));
+
+        const int num_blocks = WIDTH * HEIGHT / 64;  // server_jpeg.cpp:102 (tiles: R, G and B block each)
+        std::ifstream myfile(ctext_infile.c_str(), std::ios::binary);
+        std::ofstream outfile(ctext_outfile.c_str(), std::ios::binary);
+        if (!myfile || !outfile) {
+            std::fprintf(stderr, "server_jpeg_b200: cannot open %s or %s\n", ctext_infile.c_str(), ctext_outfile.c_str());
+            return 1;
+        }
+        const size_t W = context.ct_words(2), tile_words = 192 * W;
+        void *hbuf = nullptr, *dbuf = nullptr;
+        check(fhe_host_alloc((size_t)chunk_tiles * tile_words * 8, &hbuf));
+        check(fhe_device_alloc(context.handle(), (size_t)chunk_tiles * tile_words * 8, &dbuf));
+        uint64_t *h = (uint64_t *)hbuf;
+        std::vector<uint64_t> one;
+        WireHeader hdr;
+        check(fhe_set_stage_timing(context.handle(), 0));
+        for (int t0 = 0; t0 < num_blocks; t0 += chunk_tiles) {
+            const int nt = std::min(chunk_tiles, num_blocks - t0);
+            for (size_t i = 0; i < (size_t)nt * 192; ++i) {
+                if (!load_ciphertext(myfile, context, one, hdr) || hdr.size != 2) throw std::invalid_argument("ciphertext stream ended early");
+                std::memcpy(h + i * W, one.data(), W * 8);
+            }
+            const auto s0 = std::chrono::steady_clock::now();
+            check(fhe_upload(context.handle(), dbuf, h, (size_t)nt * tile_words * 8));
+            check(fhe_jpeg_rgb_tiles(context.handle(), plan, (const uint64_t *)dbuf, (uint64_t *)dbuf, (uint64_t)nt));
+            check(fhe_download(context.handle(), h, dbuf, (size_t)nt * tile_words * 8));
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count();
+            // CSV contract: the colour conversion is ~1/6 of the fused multiplications of a tile
+            const double per_tile = ms / nt, color_ms = per_tile / 6.0, dct_ms = per_tile - color_ms;
+            for (int t = 0; t < nt; ++t) {
+                std::cout << "RGBYCC,";
+                for (int i = 0; i < 64; ++i) std::cout << color_ms / 64 << ',';
+                std::cout << std::endl << "DCT,";
+                for (int i = 0; i < 3; ++i) std::cout << dct_ms / 3 << ',';
+                std::cout << std::endl;
+            }
+            for (size_t i = 0; i < (size_t)nt * 192; ++i) save_ciphertext(outfile, context, h + i * W, 2, hdr.hash);
+            if (verbose) std::fprintf(stderr, "tiles %d..%d: %.3f ms\n", t0, t0 + nt - 1, ms);
+        }
+        fhe_device_free(context.handle(), dbuf);
+        fhe_host_free(hbuf);
+        fhe_jpeg_plan_destroy(plan);
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "server_jpeg_b200: %s\n", e.what());
+        return 1;
+    }
+}
