@@ -1,0 +1,143 @@
+"""server_resize_b200 / server_decode_b200: the reference's homo/server_resize.cpp and
+homo/server_decode.cpp re-hosted on libfhe_b200 (same files, flags, stdout labels; wire format of
+host/seal_wire_b200.hpp).  CPU: build, flag handling, no CPU fallback.  GPU: the binaries' output
+streams equal the oracle's op-by-op graphs bit for bit (the public scalars the reference encrypts on
+the server are transparent encryptions here, which the oracle is given as inputs)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import PKG_NAME, ROOT
+from test_host_resize_decode import resize_bicubic_oracle
+from test_server_jpeg import wire_load_all, wire_save
+
+LIBDIR = os.path.join(ROOT, PKG_NAME)
+
+
+def build(pkg, name, headers):
+    pkg.build()
+    src, exe = os.path.join(LIBDIR, "server", name + ".cpp"), os.path.join(LIBDIR, "server", name)
+    deps = [src, os.path.join(ROOT, "include", "fhe_b200.h"), os.path.join(LIBDIR, "server", "cli_b200.hpp")] + [
+        os.path.join(LIBDIR, "host", h) for h in headers]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-o", exe, src, "-L" + LIBDIR,
+                               "-lfhe_b200", "-Wl,-rpath," + LIBDIR])
+    return exe
+
+
+def resize_exe(pkg):
+    return build(pkg, "server_resize_b200", ("seal_b200.hpp", "fhe_resize_b200.hpp", "seal_wire_b200.hpp"))
+
+
+def decode_exe(pkg):
+    return build(pkg, "server_decode_b200", ("seal_b200.hpp", "fhe_decode_b200.hpp", "seal_wire_b200.hpp"))
+
+
+def test_servers_build_and_handle_flags(pkg, tmp_path):
+    os.makedirs(tmp_path / "keys")
+    (tmp_path / "keys" / "params.txt").write_text("5 6 3 16384\n")
+    rexe, dexe = resize_exe(pkg), decode_exe(pkg)
+    for exe in (rexe, dexe):
+        assert subprocess.run([exe, "--help"], capture_output=True, text=True, cwd=tmp_path).returncode == 0
+        r = subprocess.run([exe, "--bogus"], capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode == 1 and "error parsing options" in r.stdout
+    r = subprocess.run([rexe, "--bicubic"], capture_output=True, text=True, cwd=tmp_path)
+    assert r.returncode == 1 and "Please enter the width/height" in r.stdout     # server_resize.cpp:72-75
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([rexe, "--bicubic", "-w", "3", "-h", "3", "--cmod", "2048"], capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode == 1 and "no usable CUDA device" in r.stderr
+        (tmp_path / "keys" / "params.txt").write_text("2 1 1 0 0\n")
+        r = subprocess.run([dexe, "--cmod", "2048"], capture_output=True, text=True, cwd=tmp_path)
+        assert r.returncode == 1 and "no usable CUDA device" in r.stderr
+
+
+def transparent(o, value):
+    ct = np.zeros(o.ct_words(2), dtype=np.uint64)
+    o.add_plain(ct, o.encode(value))
+    return ct
+
+
+@pytest.mark.gpu
+def test_server_resize_matches_oracle_on_gpu(pkg, oracle_mod, tmp_path):
+    exe = resize_exe(pkg)
+    n, ow, oh, dw, dh = 2048, 5, 6, 3, 3
+    o = oracle_mod.Oracle(n, oracle_mod.default_coeff_modulus(n), 1 << 14, 64, 32)
+    k, W = o.k, o.ct_words(2)
+    os.makedirs(tmp_path / "keys")
+    os.makedirs(tmp_path / "image")
+    (tmp_path / "keys" / "params.txt").write_text(f"{ow} {oh} 3 16384\n")
+    src = o.fill_uniform(0, ow * oh * 3, 2, 0xAB5)
+    with open(tmp_path / "image" / "nothingpersonnel.txt", "wb") as f:
+        for i in range(ow * oh * 3):
+            wire_save(f, src[i * W:(i + 1) * W], 2, k, n)
+    # the fractions the server encrypts (transparently), in the reference's call order: x then y per pixel
+    fr = []
+    for y in range(dh):
+        v = np.float32(np.float64(np.float32(y) / np.float32(dh - 1) * np.float32(oh)) - 0.5)
+        for x in range(dw):
+            u = np.float32(np.float64(np.float32(x) / np.float32(dw - 1) * np.float32(ow)) - 0.5)
+            fr.append(transparent(o, float(u - np.floor(u))))
+            fr.append(transparent(o, float(v - np.floor(v))))
+    want, nf = resize_bicubic_oracle(o, src, ow, oh, dw, dh, np.concatenate(fr))
+    assert nf == 2 * dw * dh
+    outs = {}
+    for mode in ("batched", "per-pixel"):
+        args = [exe, "--bicubic", "-w", str(dw), "-h", str(dh), "--cmod", str(n), "--ncoeff", "64", "--fcoeff", "32"]
+        if mode == "per-pixel":
+            args.append("--per-pixel")
+        r = subprocess.run(args, capture_output=True, text=True, cwd=tmp_path, timeout=900)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert r.stdout.startswith("Cubic,") and len(r.stdout.strip().rstrip(",").split(",")) == 1 + 15 * dw * dh
+        got = wire_load_all(tmp_path / "image" / "zoop.txt", k, n)
+        assert len(got) == dw * dh * 3 and all(g.size == o.ct_words(6) for g in got)
+        outs[mode] = np.concatenate(got)
+    assert (outs["batched"] == want).all()
+    assert (outs["per-pixel"] == want).all()
+
+
+@pytest.mark.gpu
+def test_server_decode_matches_oracle_on_gpu(pkg, oracle_mod, tmp_path):
+    exe = decode_exe(pkg)
+    n, width, height, pairs = 2048, 2, 1, [2, 1, 0]
+    order, degree, delta = 8, 2, 0.25
+    o = oracle_mod.Oracle(n, oracle_mod.default_coeff_modulus(n), 1 << 14, 64, 32)
+    k, W, npos = o.k, o.ct_words(2), width * height
+    os.makedirs(tmp_path / "keys")
+    os.makedirs(tmp_path / "image")
+    (tmp_path / "keys" / "params.txt").write_text(f"{width} {height} {pairs[0]} {pairs[1]} {pairs[2]}\n")
+    recs = o.fill_uniform(0, 2 * sum(pairs), 2, 0xDEC0)
+    with open(tmp_path / "image" / "nothingpersonnel.txt", "wb") as f:
+        for i in range(2 * sum(pairs)):
+            wire_save(f, recs[i * W:(i + 1) * W], 2, k, n)
+    r = subprocess.run([exe, "--cmod", str(n), "--ncoeff", "64", "--fcoeff", "32", "--order", str(order), "--degree",
+                        str(degree), "--delta", str(delta)], capture_output=True, text=True, cwd=tmp_path, timeout=900)
+    assert r.returncode == 0, r.stdout + r.stderr
+    got = wire_load_all(tmp_path / "image" / "zoop.txt", k, n)
+    assert len(got) == npos * 3
+    # oracle: server_decode.cpp:118-137 with the homomorphic approximated_step
+    zero = np.zeros(W, dtype=np.uint64)                      # transparent encrypt(encode(0))
+    zeros = np.tile(zero, 2 * degree * npos)
+    rec, chans = 0, []
+    for ch in range(3):
+        index = zero.copy()
+        channel = [zero.copy() for _ in range(npos)]
+        sizes = [2] * npos
+        for _ in range(pairs[ch]):
+            elem, count = recs[rec * W:(rec + 1) * W].copy(), recs[(rec + 1) * W:(rec + 2) * W].copy()
+            rec += 2
+            run, rs = o.approximated_step(elem, index, count, order, degree, delta, npos, zeros)
+            assert rs == 22
+            for p in range(npos):
+                big = np.zeros(o.ct_words(22), dtype=np.uint64)
+                big[: channel[p].size] = channel[p]
+                o.add(big, run[p * o.ct_words(22):(p + 1) * o.ct_words(22)].copy(), 22)
+                channel[p], sizes[p] = big, 22
+            o.add(index, count)
+        chans.append(channel)
+    for p in range(npos):
+        for ch in range(3):
+            assert got[p * 3 + ch].size == chans[ch][p].size
+            assert (got[p * 3 + ch] == chans[ch][p]).all(), (p, ch)
