@@ -38,8 +38,18 @@ constexpr int BICUBIC = 1;   // fhe_resize.h:15
 namespace detail {
 // The bodies of Cubic and Linear, written once for any ciphertext type the Evaluator overloads
 // (one seal-style Ciphertext, or a CiphertextBatch = the same graph on a whole row of pixels).
+// fhe_resize.h:174-175: t2 = square(t); "t3" = multiply(t, t) (sic: t*t, not t^3)
 template <class CT>
-inline void cubic_body(CT &result, CT &A, CT &B, CT &C, CT &D, CT &t, Evaluator &evaluator, FractionalEncoder &encoder)
+inline void cubic_powers(const CT &t, CT &t2, CT &t3, Evaluator &evaluator)
+{
+    t2 = t;
+    evaluator.square(t2);
+    t3 = t;
+    evaluator.multiply(t3, t);
+}
+template <class CT>
+inline void cubic_body(CT &result, CT &A, CT &B, CT &C, CT &D, CT &t, Evaluator &evaluator, FractionalEncoder &encoder,
+                       const std::pair<CT, CT> *powers = nullptr)
 {
     CT a, b, c, d;
     CT boaz1(A);
@@ -67,8 +77,13 @@ inline void cubic_body(CT &result, CT &A, CT &B, CT &C, CT &D, CT &t, Evaluator 
 
     d = B;
 
-    CT t2(t); evaluator.square(t2);
-    CT t3(t); evaluator.multiply(t3, t);  // sic: t*t (fhe_resize.h:175)
+    CT t2, t3;
+    if (powers) {  // square(t) and t*t are functions of t alone: a caller may compute them once per t
+        t2 = powers->first;
+        t3 = powers->second;
+    } else {
+        cubic_powers(t, t2, t3, evaluator);
+    }
 
     evaluator.multiply(a, t3);
     evaluator.multiply(b, t2);
@@ -118,9 +133,10 @@ inline void Linear(Ciphertext &result, Ciphertext &A, Ciphertext &B, Ciphertext 
 }
 // the same graphs on `count` independent inputs at once (no timing output: not a reference call)
 inline void Cubic(CiphertextBatch &result, CiphertextBatch &A, CiphertextBatch &B, CiphertextBatch &C, CiphertextBatch &D,
-                  CiphertextBatch &t, Evaluator &evaluator, FractionalEncoder &encoder)
+                  CiphertextBatch &t, Evaluator &evaluator, FractionalEncoder &encoder,
+                  const std::pair<CiphertextBatch, CiphertextBatch> *powers = nullptr)
 {
-    detail::cubic_body(result, A, B, C, D, t, evaluator, encoder);
+    detail::cubic_body(result, A, B, C, D, t, evaluator, encoder, powers);
 }
 inline void Linear(CiphertextBatch &result, CiphertextBatch &A, CiphertextBatch &B, CiphertextBatch &t, Evaluator &evaluator,
                    FractionalEncoder &encoder)
@@ -325,7 +341,8 @@ inline void ResizeImageBatched(const CiphertextSource &load, int original_width,
         std::vector<std::vector<CiphertextBatch>> tap((size_t)taps, std::vector<CiphertextBatch>());
         for (auto &row : tap)
             for (int cidx = 0; cidx < taps; ++cidx) row.emplace_back(ctx, count, 2);
-        CiphertextBatch xfract(ctx, count, 2), yfract(ctx, count, 2);
+        // one encrypted fraction pair per output pixel; the three channels share it
+        CiphertextBatch xf1(ctx, (size_t)dest_width, 2), yf1(ctx, (size_t)dest_width, 2);
         const int off = inter == BICUBIC ? -1 : 0;
         const int yint = int(v);
         for (int x = 0; x < dest_width; ++x) {
@@ -334,10 +351,8 @@ inline void ResizeImageBatched(const CiphertextSource &load, int original_width,
             Ciphertext xf, yf;
             encryptor.encrypt(encoder.encode(u - std::floor(u)), xf);
             encryptor.encrypt(encoder.encode(v - std::floor(v)), yf);
-            for (int ch = 0; ch < 3; ++ch) {
-                xfract.set((size_t)x * 3 + ch, xf);
-                yfract.set((size_t)x * 3 + ch, yf);
-            }
+            xf1.set((size_t)x, xf);
+            yf1.set((size_t)x, yf);
             for (int r = 0; r < taps; ++r)
                 for (int cidx = 0; cidx < taps; ++cidx) {
                     int px = std::min(std::max(xint + off + cidx, 0), srcImage.width - 1);
@@ -346,11 +361,27 @@ inline void ResizeImageBatched(const CiphertextSource &load, int original_width,
                     for (int ch = 0; ch < 3; ++ch) tap[(size_t)r][(size_t)cidx].set((size_t)x * 3 + ch, pixel[(size_t)ch]);
                 }
         }
+        auto per_channel = [&](const CiphertextBatch &one) {  // element x -> elements 3x, 3x+1, 3x+2
+            CiphertextBatch r(ctx, count, one.size());
+            const size_t w = ctx.ct_words(one.size()) * sizeof(uint64_t);
+            for (int ch = 0; ch < 3; ++ch)
+                check(fhe_device_copy_2d(ctx.handle(), r.device_data() + (size_t)ch * ctx.ct_words(one.size()), 3 * w,
+                                         one.device_data(), w, w, one.count()));
+            return r;
+        };
+        CiphertextBatch xfract = per_channel(xf1), yfract = per_channel(yf1);
         CiphertextBatch out;
         if (inter == BICUBIC) {
+            // the powers of the fractions are the same ciphertexts in every Cubic that uses them (4 rows x 3
+            // channels for x, 3 channels for y): computed once per output pixel, bit-identical
+            CiphertextBatch x2, x3, y2, y3;
+            detail::cubic_powers(xf1, x2, x3, evaluator);
+            detail::cubic_powers(yf1, y2, y3, evaluator);
+            const std::pair<CiphertextBatch, CiphertextBatch> xp(per_channel(x2), per_channel(x3)), yp(per_channel(y2), per_channel(y3));
             std::vector<CiphertextBatch> col(4);
-            for (int r = 0; r < 4; ++r) Cubic(col[(size_t)r], tap[(size_t)r][0], tap[(size_t)r][1], tap[(size_t)r][2], tap[(size_t)r][3], xfract, evaluator, encoder);
-            Cubic(out, col[0], col[1], col[2], col[3], yfract, evaluator, encoder);
+            for (int r = 0; r < 4; ++r)
+                Cubic(col[(size_t)r], tap[(size_t)r][0], tap[(size_t)r][1], tap[(size_t)r][2], tap[(size_t)r][3], xfract, evaluator, encoder, &xp);
+            Cubic(out, col[0], col[1], col[2], col[3], yfract, evaluator, encoder, &yp);
         } else {
             CiphertextBatch col0, col1;
             Linear(col0, tap[0][0], tap[0][1], xfract, evaluator, encoder);
