@@ -30,12 +30,10 @@ inline void fresh_encrypt(Encryptor &e, const Plaintext &p, CiphertextBatch &res
 }
 // shared body: the two series differ only in the sign of every coefficient.  CT = Ciphertext (the
 // reference's call) or CiphertextBatch (the same graph on many independent arguments at once).
+// the series itself; `res` holds the fresh encryption of 0.0 on entry (fhe_decode.h:54, :134)
 template <class CT>
-inline void taylor_3pi2(CT &x, CT &res, double sign, Evaluator &evaluator, FractionalEncoder &encoder,
-                        Encryptor &encryptor)
+inline void taylor_3pi2_core(CT &x, CT &res, double sign, Evaluator &evaluator, FractionalEncoder &encoder)
 {
-    fresh_encrypt(encryptor, encoder.encode(0.0), res, x);
-
     CT shifted_x(x);
     evaluator.add_plain(shifted_x, encoder.encode(-3 * M_PI / 2.0));
 
@@ -78,6 +76,13 @@ inline void taylor_3pi2(CT &x, CT &res, double sign, Evaluator &evaluator, Fract
     evaluator.add(res, power6);
     evaluator.add(res, power8);
     evaluator.add(res, power10);
+}
+template <class CT>
+inline void taylor_3pi2(CT &x, CT &res, double sign, Evaluator &evaluator, FractionalEncoder &encoder,
+                        Encryptor &encryptor)
+{
+    fresh_encrypt(encryptor, encoder.encode(0.0), res, x);
+    taylor_3pi2_core(x, res, sign, evaluator, encoder);
 }
 }  // namespace detail
 
@@ -138,6 +143,75 @@ inline void approximated_step(CT &amplitude, CT &index, CT &count, int order, in
         evaluator.multiply(c, amplitude);
         run.push_back(c);
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// B200-first variant of approximated_step: identical arithmetic and identical results for ANY
+// Encryptor (the server-side encryptions are drawn in the reference's call order: sin then cos for
+// j = 1..degree inside i = 0..width*height-1), but the width*height*degree sine and cosine series --
+// the expensive part, 15 ciphertext products each -- run as TWO batched series over all (i, j), and
+// the closing products as one batched call per step.  Elements are stored j-major so that the
+// per-j plaintext factors act on contiguous slices.
+inline void approximated_step_batched(Ciphertext &amplitude, Ciphertext &index, Ciphertext &count, int order, int degree,
+                                      double delta, int width, int height, std::vector<Ciphertext> &run,
+                                      Evaluator &evaluator, FractionalEncoder &encoder, Encryptor &encryptor)
+{
+    const Context &ctx = evaluator.context();
+    const size_t npos = (size_t)width * height, E = npos * (size_t)degree;
+    Ciphertext b(count);
+    evaluator.multiply_plain(b, encoder.encode(0.5));
+    Ciphertext offset(index);
+    evaluator.add(offset, b);
+    evaluator.add_plain(offset, encoder.encode(-0.5));
+    evaluator.negate(offset);
+    evaluator.add_plain(b, encoder.encode(delta - 0.5));
+    if (degree < 1 || npos == 0) {  // no series: c = b / order, times amplitude
+        for (size_t i = 0; i < npos; ++i) {
+            Ciphertext c(b);
+            evaluator.multiply_plain(c, encoder.encode(1.0 / ((double)order)));
+            evaluator.multiply(c, amplitude);
+            run.push_back(c);
+        }
+        return;
+    }
+    CiphertextBatch sin_arg(ctx, E, 2), cos_arg(ctx, E, 2), sin_f(ctx, E, 2), cos_f(ctx, E, 2);
+    Ciphertext z;
+    for (size_t i = 0; i < npos; ++i)
+        for (int j = 1; j <= degree; ++j) {
+            const size_t e = (size_t)(j - 1) * npos + i;
+            cos_arg.set(e, offset);                                   // Ciphertext cos_arg(offset);
+            evaluator.add_plain(offset, encoder.encode((double)i));   // :229, inside the j loop
+            encryptor.encrypt(encoder.encode(0.0), z);                // homomorphic_sin's res (:54)
+            sin_f.set(e, z);
+            encryptor.encrypt(encoder.encode(0.0), z);                // homomorphic_cos's res (:134)
+            cos_f.set(e, z);
+        }
+    for (int j = 1; j <= degree; ++j) {
+        const double arg_factor = ((float)j) * M_PI / ((double)order);
+        Ciphertext sa(b);
+        evaluator.multiply_plain(sa, encoder.encode(arg_factor));     // the same ciphertext for every i
+        for (size_t i = 0; i < npos; ++i) sin_arg.set((size_t)(j - 1) * npos + i, sa);
+        CiphertextBatch cj = cos_arg.slice((size_t)(j - 1) * npos, npos);
+        evaluator.multiply_plain(cj, encoder.encode(arg_factor));     // in place on the slice
+    }
+    detail::taylor_3pi2_core(sin_arg, sin_f, 1.0, evaluator, encoder);
+    detail::taylor_3pi2_core(cos_arg, cos_f, -1.0, evaluator, encoder);
+    evaluator.multiply(sin_f, cos_f);                                  // term = sin_factor * cos_factor
+    CiphertextBatch c(ctx, npos, 2);
+    {
+        Ciphertext c0(b);
+        evaluator.multiply_plain(c0, encoder.encode(1.0 / ((double)order)));
+        for (size_t i = 0; i < npos; ++i) c.set(i, c0);
+    }
+    for (int j = 1; j <= degree; ++j) {
+        CiphertextBatch tj = sin_f.slice((size_t)(j - 1) * npos, npos);
+        evaluator.multiply_plain(tj, encoder.encode(2.0 / (M_PI * ((float)j))));
+        evaluator.add(c, tj);
+    }
+    CiphertextBatch amp(ctx, npos, amplitude.size());
+    for (size_t i = 0; i < npos; ++i) amp.set(i, amplitude);
+    evaluator.multiply(c, amp);
+    for (size_t i = 0; i < npos; ++i) run.push_back(c.get(i));
 }
 
 }  // namespace seal_b200

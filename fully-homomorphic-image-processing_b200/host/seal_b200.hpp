@@ -238,9 +238,10 @@ public:
     }
     CiphertextBatch(const CiphertextBatch &o) : ctx_(o.ctx_), count_(o.count_), size_(o.size_)
     {
-        if (!o.arena_) return;
-        arena_ = std::make_shared<Arena>(*ctx_, o.arena_->words());
-        check(fhe_device_copy(ctx_->handle(), arena_->data(), o.arena_->data(), o.arena_->words() * sizeof(uint64_t)));
+        if (!o.arena_) return;  // copying a slice makes an independent batch of just that range
+        const size_t words = ctx_->ct_words(size_) * count_;
+        arena_ = std::make_shared<Arena>(*ctx_, words);
+        check(fhe_device_copy(ctx_->handle(), arena_->data(), o.device_data(), words * sizeof(uint64_t)));
     }
     CiphertextBatch(CiphertextBatch &&) noexcept = default;
     CiphertextBatch &operator=(const CiphertextBatch &o)
@@ -257,8 +258,21 @@ public:
     uint32_t size() const { return size_; }
     bool valid() const { return arena_ != nullptr; }
     const Context *context() const { return ctx_; }
-    uint64_t *device_data() const { return arena_ ? arena_->data() : nullptr; }
-    uint64_t *element(size_t i) const { return arena_->data() + i * ctx_->ct_words(size_); }
+    uint64_t *device_data() const { return arena_ ? arena_->data() + off_ : nullptr; }
+    uint64_t *element(size_t i) const { return device_data() + i * ctx_->ct_words(size_); }
+    // elements [first, first + count) as a batch SHARING this storage (in-place Evaluator ops on the
+    // slice -- multiply_plain, add, negate ... -- act on this batch; size-changing ops detach it)
+    CiphertextBatch slice(size_t first, size_t count) const
+    {
+        if (first + count > count_) throw std::invalid_argument("batch slice out of range");
+        CiphertextBatch v;
+        v.ctx_ = ctx_;
+        v.arena_ = arena_;
+        v.count_ = count;
+        v.size_ = size_;
+        v.off_ = off_ + first * ctx_->ct_words(size_);
+        return v;
+    }
     // element i <- c (device copy); sizes must agree
     void set(size_t i, const Ciphertext &c)
     {
@@ -282,13 +296,13 @@ public:
         check(fhe_device_copy_2d(ctx_->handle(), r.device_data(), wn, device_data(), wo, wo, count_));
         return r;
     }
-    void upload(const uint64_t *host) { check(fhe_upload(ctx_->handle(), device_data(), host, arena_->words() * 8)); }
-    void download(uint64_t *host) const { check(fhe_download(ctx_->handle(), host, device_data(), arena_->words() * 8)); }
+    void upload(const uint64_t *host) { check(fhe_upload(ctx_->handle(), device_data(), host, ctx_->ct_words(size_) * count_ * 8)); }
+    void download(uint64_t *host) const { check(fhe_download(ctx_->handle(), host, device_data(), ctx_->ct_words(size_) * count_ * 8)); }
 
 private:
     const Context *ctx_ = nullptr;
     std::shared_ptr<Arena> arena_;
-    size_t count_ = 0;
+    size_t count_ = 0, off_ = 0;
     uint32_t size_ = 0;
 };
 

@@ -151,6 +151,16 @@ int main(int argc, char **argv)
             }
         }
 
+        // batched step == the reference-order step, with the same stream of server-side encryptions
+        {
+            next_zero = 8;
+            Ciphertext amp2 = ct_at(5), idx2 = ct_at(6), cnt2 = ct_at(7);
+            std::vector<Ciphertext> run2;
+            approximated_step_batched(amp2, idx2, cnt2, 8, 2, 0.25, 2, 1, run2, evaluator, encoder, zeros);
+            REQUIRE(run2.size() == 2 && next_zero == 16);
+            REQUIRE(same(run[0], run2[0]) && same(run[1], run2[1]));
+        }
+
         // the key-less deterministic Encryptor: (Delta*m, 0) decrypts to m and is accepted by the graphs
         Encryptor transparent(ctx);
         Ciphertext tz;

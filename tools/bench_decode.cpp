@@ -1,0 +1,55 @@
+// bench_decode.cpp -- BASELINE.json config 5 (server_decode homomorphic step approximation, 8x8 blocks
+// = 64 positions, n=8192, deep multiply) on one B200 through the C++ host layer:
+// approximated_step_batched (host/fhe_decode_b200.hpp) on synthetic uniform ciphertexts, transparent
+// server-side encryptions.  One run-length pair expands to width*height ciphertexts of size 22 through
+// 2 * positions * degree Taylor series (15 ciphertext products each, sizes up to 11).
+// Not the headline bench (bench.py).  Usage: bench_decode [n] [positions] [degree] [order] -> JSON line
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../fully-homomorphic-image-processing_b200/host/fhe_decode_b200.hpp"
+
+using namespace seal_b200;
+
+int main(int argc, char **argv)
+{
+    try {
+        const uint32_t n = argc > 1 ? (uint32_t)std::atoi(argv[1]) : 8192;
+        const int npos = argc > 2 ? std::atoi(argv[2]) : 64, degree = argc > 3 ? std::atoi(argv[3]) : 12;
+        const int order = argc > 4 ? std::atoi(argv[4]) : 64;
+        Context ctx(n);
+        Evaluator evaluator(ctx);
+        FractionalEncoder encoder(ctx, 100, 100);
+        Encryptor encryptor(ctx);
+        Ciphertext amplitude(ctx, 2), index(ctx, 2), count(ctx, 2);
+        check(fhe_fill_uniform(ctx.handle(), amplitude.device_data(), 0, 1, 2, 0xDEC));
+        check(fhe_fill_uniform(ctx.handle(), index.device_data(), 1, 1, 2, 0xDEC));
+        check(fhe_fill_uniform(ctx.handle(), count.device_data(), 2, 1, 2, 0xDEC));
+        double best = 1e30;
+        unsigned long long launches = 0;
+        size_t out_size = 0;
+        for (int rep = 0; rep < 2; ++rep) {
+            std::vector<Ciphertext> run;
+            const uint64_t l0 = fhe_launch_count(ctx.handle());
+            ctx.sync();
+            auto t0 = std::chrono::steady_clock::now();
+            approximated_step_batched(amplitude, index, count, order, degree, 0.5, npos, 1, run, evaluator, encoder, encryptor);
+            ctx.sync();
+            const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (s < best) best = s;
+            launches = fhe_launch_count(ctx.handle()) - l0;
+            out_size = run.at(0).size();
+        }
+        const double series = 2.0 * npos * degree, products = series * 15 + (double)npos * degree + npos;
+        std::printf("{\"what\": \"approximated_step_batched (homomorphic RLE step, fhe_decode.h:202-242), n=%u k=%u, "
+                    "%d positions, degree %d, order %d, synthetic ciphertexts, transparent server-side encryptions\", "
+                    "\"seconds_per_run_length_pair\": %.4f, \"taylor_series_per_s\": %.1f, \"ct_products_per_s\": %.1f, "
+                    "\"out_ct_size\": %zu, \"kernel_launches\": %llu}\n",
+                    n, ctx.coeff_mod_count(), npos, degree, order, best, series / best, products / best, out_size, launches);
+        return 0;
+    } catch (const std::exception &e) {
+        std::fprintf(stderr, "exception: %s\n", e.what());
+        return 1;
+    }
+}
