@@ -132,6 +132,30 @@ def test_relinearize_vs_oracle(gpu, oracle_mod, n, dbc, size, n_ct):
     ctx.close()
 
 
+def test_multiply_edge_cases(gpu, oracle_mod):
+    """Empty batches, size-1 operands (a bare polynomial, as SEAL allows), the largest sizes of the
+    decode graph (21 x 2 -> 22, fhe_decode.h:239), and rejected arguments."""
+    n = 2048
+    q = oracle_mod.default_coeff_modulus(n)
+    ctx, o = gpu.Context(n, q), oracle_mod.Oracle(n, q)
+    a, b = o.fill_uniform(1, 1, 21, 3), o.fill_uniform(2, 1, 2, 4)
+    da, db = ctx.to_device(a), ctx.to_device(b)
+    dd = ctx.alloc(ctx.ct_bytes(22))
+    ctx.multiply(da, 21, db, 2, dd, 0)            # n_ct = 0: nothing to do
+    ctx.multiply(da, 21, db, 2, dd, 1)
+    assert (fetch(ctx, dd, ctx.ct_words(22)) == o.multiply(a, 21, b, 2)).all()
+    ctx.multiply(da, 1, db, 2, dd, 1)             # size 1 x size 2 -> size 2
+    assert (fetch(ctx, dd, ctx.ct_words(2)) == o.multiply(a[: ctx.ct_words(1)].copy(), 1, b, 2)).all()
+    for bad in (lambda: ctx.multiply(da, 0, db, 2, dd, 1), lambda: ctx.multiply(da, 33, db, 2, dd, 1),
+                lambda: ctx.multiply(0, 2, db, 2, dd, 1), lambda: ctx.multiply(da, 2, db, 2, 0, 1),
+                lambda: ctx.square(0, 2, dd, 1)):
+        with pytest.raises(gpu.FheError):
+            bad()
+    for d in (da, db, dd):
+        ctx.free(d)
+    ctx.close()
+
+
 def test_multiply_then_relinearize_decrypts(gpu, oracle_mod):
     n, dbc = 4096, 30
     q = oracle_mod.default_coeff_modulus(n)
