@@ -25,7 +25,9 @@ enum DctConst {
 
 // One 1-D pass on d[0..7].  Inputs < INB*q.  Outputs: d0,d4 < 8*INB*q; d2,d6 < 10q; odd < 20q.
 // Needs 8*INB <= FHE_BMAX (every mulc argument stays below 2^63).
-template <int INB>
+// c: the 12 constants, constant i at c[i * CS] (CS = 1: a thread-private array; CS = DCT_TILE: a
+// shared-memory table [12][DCT_TILE] addressed from the thread's own position).
+template <int INB, int CS = 1>
 FHE_HD void dct8_pass(u64 *d, const W2 *c, u64 q, u64 n2q)
 {
     static_assert(8 * INB <= 256, "dct8_pass: lazy bound exceeds 2^63");
@@ -38,20 +40,20 @@ FHE_HD void dct8_pass(u64 *d, const W2 *c, u64 q, u64 n2q)
     u64 tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2 + o2;
     d[0] = tmp10 + tmp11;
     d[4] = tmp10 - tmp11 + o4;
-    u64 z1 = mulc(tmp12 + tmp13, c[C_0541196100], n2q);
-    d[2] = z1 + mulc(tmp13, c[C_0765366865], n2q);
-    d[6] = z1 + mulc(tmp12, c[C_M1847759065], n2q);
+    u64 z1 = mulc(tmp12 + tmp13, c[C_0541196100 * CS], n2q);
+    d[2] = z1 + mulc(tmp13, c[C_0765366865 * CS], n2q);
+    d[6] = z1 + mulc(tmp12, c[C_M1847759065 * CS], n2q);
     z1 = tmp4 + tmp7;
     u64 z2 = tmp5 + tmp6, z3 = tmp4 + tmp6, z4 = tmp5 + tmp7;
-    u64 z5 = mulc(z3 + z4, c[C_1175875602], n2q);
-    tmp4 = mulc(tmp4, c[C_0298631336], n2q);
-    tmp5 = mulc(tmp5, c[C_2053119869], n2q);
-    tmp6 = mulc(tmp6, c[C_3072711026], n2q);
-    tmp7 = mulc(tmp7, c[C_1501321110], n2q);
-    z1 = mulc(z1, c[C_M0899976223], n2q);
-    z2 = mulc(z2, c[C_M2562915447], n2q);
-    z3 = mulc(z3, c[C_M1961570560], n2q) + z5;
-    z4 = mulc(z4, c[C_M0390180644], n2q) + z5;
+    u64 z5 = mulc(z3 + z4, c[C_1175875602 * CS], n2q);
+    tmp4 = mulc(tmp4, c[C_0298631336 * CS], n2q);
+    tmp5 = mulc(tmp5, c[C_2053119869 * CS], n2q);
+    tmp6 = mulc(tmp6, c[C_3072711026 * CS], n2q);
+    tmp7 = mulc(tmp7, c[C_1501321110 * CS], n2q);
+    z1 = mulc(z1, c[C_M0899976223 * CS], n2q);
+    z2 = mulc(z2, c[C_M2562915447 * CS], n2q);
+    z3 = mulc(z3, c[C_M1961570560 * CS], n2q) + z5;
+    z4 = mulc(z4, c[C_M0390180644 * CS], n2q) + z5;
     d[7] = tmp4 + z1 + z3;
     d[5] = tmp5 + z2 + z4;
     d[3] = tmp6 + z2 + z3;
@@ -73,18 +75,20 @@ FHE_HD void dct_row_load(int r, int lane, const u64 *__restrict__ in, size_t ct_
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = in[(size_t)(8 * r + i) * ct_stride + lane];
 }
+template <int CS = 1>
 FHE_HD void dct_row_compute(int r, int lane, u64 *d, u64 *sbuf, const W2 *c, u64 q, u64 n2q)
 {
-    dct8_pass<DCT_ROW_INB>(d, c, q, n2q);
+    dct8_pass<DCT_ROW_INB, CS>(d, c, q, n2q);
 #pragma unroll
     for (int i = 0; i < 8; ++i) sbuf[(8 * r + i) * DCT_TILE + lane] = d[i];
 }
+template <int CS = 1>
 FHE_HD void dct_row_phase(int r, int lane, const u64 *__restrict__ in, size_t ct_stride, u64 *sbuf,
                           const W2 *c, u64 q, u64 n2q)
 {
     u64 d[8];
     dct_row_load(r, lane, in, ct_stride, d);
-    dct_row_compute(r, lane, d, sbuf, c, q, n2q);
+    dct_row_compute<CS>(r, lane, d, sbuf, c, q, n2q);
 }
 
 // Column phase for (column col, lane): 1-D pass down the column, then one multiplication per
@@ -92,13 +96,14 @@ FHE_HD void dct_row_phase(int r, int lane, const u64 *__restrict__ in, size_t ct
 // alone when no quantisation table is attached), times n^-1 so the inverse NTT that follows skips
 // its own scaling.  Output < 5q (inverse-NTT input range).
 // s: scale constants of outputs (row i, this column), s[i * s_stride]
+template <int CS = 1>
 FHE_HD void dct_col_phase(int col, int lane, u64 *__restrict__ out, size_t ct_stride, const u64 *sbuf,
                           const W2 *c, const W2 *__restrict__ s, size_t s_stride, u64 q, u64 n2q)
 {
     u64 d[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) d[i] = sbuf[(8 * i + col) * DCT_TILE + lane];
-    dct8_pass<8 * DCT_ROW_INB>(d, c, q, n2q);
+    dct8_pass<8 * DCT_ROW_INB, CS>(d, c, q, n2q);
 #pragma unroll
     for (int i = 0; i < 8; ++i) out[(size_t)(8 * i + col) * ct_stride + lane] = mulc(d[i], s[i * s_stride], n2q);
 }

@@ -2,6 +2,7 @@
 //
 // sm_100a only.  No tensor cores: the path is 64-bit integer modular arithmetic on the
 // IMAD/ALU pipes, staged through shared memory, with coalesced HBM access (north_star).
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -116,37 +117,123 @@ k_mulplain(const u64 *in, u64 *out, const W2 *__restrict__ table, RingDev R)
 // =============================================================================================
 // CTA = 8 warps on one (limb, 32-position tile); loops over `upc` consecutive units
 // (unit = one poly of one block: 64 limb-polys, one per ciphertext of the block) so the
-// 12 + 8 constants a thread needs stay in registers across units.  (Re-reading the 8 scale
-// constants per unit from L1 and prefetching the next unit's inputs instead measured 9 % slower
-// on B200, and a 3-CTA/SM register cap spills: profiles/r01_notes.md.)
-__global__ void __launch_bounds__(256, 2)
-k_dct_pointwise(u64 *data, const W2 *__restrict__ ctab, const W2 *__restrict__ stab, RingDev R,
-                unsigned long long nunits, int upc, uint32_t blk_stride /* ciphertexts between blocks: 64 = dense */)
+// 12 + 8 constants a thread needs stay in registers across units (128 registers, 2 CTAs per SM).
+// Measured alternatives (profiles/r01_notes.md): per-thread LDG/STG of the unit instead of TMA
+// 43.3 ms per 8192 blocks against 34.3; constants in shared memory at 1024 threads per SM 45.7;
+// 64 row-sized cp.async.bulk per unit instead of one tensor box 57.0.
+//
+// The ciphertext array [ct][poly*k+limb][n] is described to the TMA unit as a
+// rank-3 u64 tensor; a unit's 64 x 32 inputs (row i = 32 consecutive NTT positions of ciphertext i
+// of the block) are ONE box {32, 1, 64}, fetched by one cp.async.bulk.tensor (SASS UTMALDG) into a
+// 16 KiB shared-memory stage and written back by one UTMASTG.  The stage is input buffer, 8x8
+// transposition buffer and output buffer at once (the row phase reads and writes rows 8r..8r+7 in
+// place, the column phase rows 8i+col).  With a ring of DCT_NSTAGE stages the loads of the next
+// units and the stores of the previous ones run in the async proxy under the arithmetic; the
+// threads issue no global loads or stores at all.  Ordering: one thread issues every copy, so its
+// own cp.async.bulk.wait_group.read is the WAR guard between a stage's store and the next load
+// into it; load completion is an mbarrier transaction count.
+constexpr int DCT_NSTAGE = 3;
+constexpr uint32_t DCT_UNIT_BYTES = 64 * DCT_TILE * sizeof(u64);
+constexpr size_t DCT_SMEM = (size_t)DCT_NSTAGE * DCT_UNIT_BYTES + 64;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    __shared__ u64 sbuf[2][64 * DCT_TILE];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "W_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@!p bra W_%=;\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 2)
+k_dct_pointwise(const __grid_constant__ CUtensorMap tmap, const W2 *__restrict__ ctab, const W2 *__restrict__ stab,
+                    RingDev R, unsigned long long nunits, int upc, uint32_t blk_stride)
+{
+    extern __shared__ __align__(128) unsigned char dsm_raw[];
+    u64 *stage = reinterpret_cast<u64 *>(dsm_raw);                         // [NSTAGE][64][TILE]
+    const uint32_t bars = smem_u32(dsm_raw + (size_t)DCT_NSTAGE * DCT_UNIT_BYTES);  // NSTAGE mbarriers
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const uint32_t n = R.n, k = R.k, tiles = n / DCT_TILE;
     const uint32_t tile = blockIdx.x % tiles, j = (blockIdx.x / tiles) % k;
     const unsigned long long ug = blockIdx.x / (tiles * k);
     const size_t pos = (size_t)tile * DCT_TILE + lane;
     const u64 q = R.limb[j].a.q, n2q = R.limb[j].a.n2q;
+    const unsigned long long u0 = ug * upc;
+    const int nu = (int)(nunits - u0 < (unsigned long long)upc ? nunits - u0 : upc);
+    // box coordinates of unit u0 + it: (position, poly * k + limb, first ciphertext of the block)
+    const int c0 = (int)(tile * DCT_TILE);
+    auto load_unit = [&](int it) {
+        const unsigned long long u = u0 + it;
+        const int b = it % DCT_NSTAGE, c1 = (int)((u & 1) * k + j), c2 = (int)((u >> 1) * blk_stride);
+        const uint32_t bar = bars + 8 * b, dst = smem_u32(stage + (size_t)b * 64 * DCT_TILE);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(DCT_UNIT_BYTES) : "memory");
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                     ::"r"(dst), "l"(&tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+    };
+    if (tid == 0) {
+        for (int b = 0; b < DCT_NSTAGE; ++b) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bars + 8 * b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap));
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int it = 0; it < DCT_NSTAGE - 1 && it < nu; ++it) load_unit(it);
     W2 c[DCT_NCONST], s[8];
 #pragma unroll
     for (int i = 0; i < DCT_NCONST; ++i) c[i] = ctab[((size_t)i * k + j) * n + pos];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = stab[((size_t)(8 * i + w) * k + j) * n + pos];
-    const size_t ct_stride = (size_t)2 * k * n;
-    for (int it = 0; it < upc; ++it) {
-        const unsigned long long u = ug * upc + it;
-        if (u >= nunits) break;
-        const unsigned long long blk = u >> 1;
-        const uint32_t poly = (uint32_t)(u & 1);
-        u64 *base = data + blk * blk_stride * ct_stride + ((size_t)poly * k + j) * n + (size_t)tile * DCT_TILE;
-        u64 *sb = sbuf[it & 1];
-        dct_row_phase(w, lane, base, ct_stride, sb, c, q, n2q);
+    for (int it = 0; it < nu; ++it) {
+        const int b = it % DCT_NSTAGE;
+        u64 *sb = stage + (size_t)b * 64 * DCT_TILE;
+        mbar_wait(bars + 8 * b, (uint32_t)(it / DCT_NSTAGE) & 1);
+        dct_row_phase(w, lane, sb, DCT_TILE, sb, c, q, n2q);
         __syncthreads();
-        dct_col_phase(w, lane, base, ct_stride, sb, c, s, 1, q, n2q);
+        dct_col_phase(w, lane, sb, DCT_TILE, sb, c, s, 1, q, n2q);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the TMA store
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long u = u0 + it;
+            const int c1 = (int)((u & 1) * k + j), c2 = (int)((u >> 1) * blk_stride);
+            asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+                         ::"l"(&tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(sb)) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the stage of unit it-1 is the one unit it+NSTAGE-1 loads into: its store (the previous
+            // bulk group of this thread) must have finished reading shared memory
+            if (it + DCT_NSTAGE - 1 < nu) {
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                load_unit(it + DCT_NSTAGE - 1);
+            }
+        }
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores done before the CTA's smem is released
+}
+
+static int fail(int code, const std::string &msg);
+// Tensor map of a ciphertext array for the kernel above (host side; the driver entry point is
+// resolved through the runtime so the library does not link libcuda directly).
+static int make_ct_tensor_map(CUtensorMap *tm, const u64 *base, uint64_t n_ct, uint32_t k, uint32_t n)
+{
+    typedef CUresult (*encode_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static encode_fn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+            return fail(FHE_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+        encode = (encode_fn)fn;
+    }
+    const cuuint64_t dims[3] = {n, 2ull * k, n_ct};
+    const cuuint64_t strides[2] = {(cuuint64_t)n * 8, (cuuint64_t)2 * k * n * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)DCT_TILE, 1, 64}, estr[3] = {1, 1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, (void *)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(FHE_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return FHE_OK;
 }
 
 // =============================================================================================
@@ -824,10 +911,34 @@ void fhe_dct_plan_destroy(fhe_dct_plan *p)
     delete p;
 }
 
+// Pointwise DCT (+quantize) of `nblocks` blocks whose first ciphertexts are `blk_stride`
+// ciphertexts apart (64 = dense; 192 = one channel of RGB tiles), in place on `data`, an array of
+// `n_ct` size-2 ciphertexts.
+static int launch_dct_pointwise(fhe_ctx *c, const fhe_dct_plan *plan, u64 *data, uint64_t nblocks, uint32_t blk_stride,
+                                uint64_t n_ct, cudaStream_t st)
+{
+    const uint32_t n = c->host.n, k = c->host.k;
+    const unsigned long long nunits = nblocks * 2;
+    // units per CTA: 32 amortise the constant loads of a CTA; fewer when that would leave the
+    // grid under a few waves of 2 CTAs per SM
+    const unsigned long long per_ug = (unsigned long long)k * (n / DCT_TILE), want = 8ull * c->sm_count;
+    int upc = 32;
+    while (upc > 1 && ((nunits + upc - 1) / upc) * per_ug < want) upc >>= 1;
+    const unsigned long long grid = ((nunits + upc - 1) / upc) * per_ug;
+    if (grid > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many blocks in one chunk");
+    CUtensorMap tm;
+    if (int rc = make_ct_tensor_map(&tm, data, n_ct, k, n)) return rc;
+    if (int rc = set_smem(k_dct_pointwise, DCT_SMEM)) return rc;
+    k_dct_pointwise<<<(unsigned)grid, 256, DCT_SMEM, st>>>(tm, plan->d_c, plan->d_s, c->dev, nunits, upc, blk_stride);
+    c->launches++;
+    CU_TRY(cudaGetLastError());
+    return FHE_OK;
+}
+
 // three kernels per chunk: forward NTT (in -> out), pointwise DCT in place, inverse NTT in place
 static int dct_chunk(fhe_ctx *c, const fhe_dct_plan *plan, const u64 *in, u64 *out, uint64_t nblocks, cudaStream_t st)
 {
-    const uint32_t n = c->host.n, k = c->host.k;
+    const uint32_t k = c->host.k;
     const uint64_t npoly = nblocks * 64 * 2 * k;
     auto mark = [&]() -> int {
         if (!c->stage_timing) return FHE_OK;
@@ -840,14 +951,7 @@ static int dct_chunk(fhe_ctx *c, const fhe_dct_plan *plan, const u64 *in, u64 *o
     if (int rc = mark()) return rc;
     if (int rc = ntt_forward(c, in, out, npoly, NTT_OUT_REDUCED, st)) return rc;
     if (int rc = mark()) return rc;
-    const unsigned long long nunits = nblocks * 2;
-    const int upc = 16;
-    const unsigned long long ugs = (nunits + upc - 1) / upc;
-    const unsigned long long grid = ugs * k * (n / DCT_TILE);
-    if (grid > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many blocks in one chunk");
-    k_dct_pointwise<<<(unsigned)grid, 256, 0, st>>>(out, plan->d_c, plan->d_s, c->dev, nunits, upc, 64);
-    c->launches++;
-    CU_TRY(cudaGetLastError());
+    if (int rc = launch_dct_pointwise(c, plan, out, nblocks, 64, nblocks * 64, st)) return rc;
     if (int rc = mark()) return rc;
     if (int rc = ntt_inverse(c, out, out, npoly, false, st)) return rc;
     return mark();

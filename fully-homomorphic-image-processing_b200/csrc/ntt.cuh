@@ -130,7 +130,6 @@ FHE_HD void inv_stage(u64 *v, int tau, const W2 *__restrict__ itw, const LimbDev
     constexpr int D = Gm::R - 1 - DD, RR = Gm::RR, half = 1 << DD;
     constexpr bool final_stage = (P == 0 && D == 0);
     static_assert(2 * inv_bound(B_IN, 0, DD) <= FHE_BMAX, "inverse lazy bound exceeds BMAX");
-    const u64 q = lp.a.q;
 #pragma unroll
     for (int g = 0; g < Gm::G; ++g) {
 #pragma unroll
@@ -142,7 +141,7 @@ FHE_HD void inv_stage(u64 *v, int tau, const W2 *__restrict__ itw, const LimbDev
             for (int lo = 0; lo < half; ++lo) {
                 const int M = mt * (2 * half) + lo;
                 const int ia = g * RR + M, ib = ia + half;
-                const u64 kq = (u64)inv_bound(B_IN, M, DD) * q;  // folds to a constant multiple of q
+                const u64 kq = bound_times_q(lp.a, inv_bound(B_IN, M, DD));  // one precomputed operand
                 const u64 U = v[ia], V = v[ib];
                 const u64 sum = U + V;
                 const u64 dif = U - V + kq;

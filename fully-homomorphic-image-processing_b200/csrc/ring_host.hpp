@@ -47,6 +47,7 @@ inline LimbArith h_limb_arith(u64 q)
 {
     LimbArith a;
     a.q = q; a.n2q = 0 - 2 * q; a.nq = 0 - q; a.q5 = 5 * q;
+    for (int i = 0; i < 4; ++i) { a.kq5[i] = (5 * q) << i; a.kq16[i] = (16 * q) << i; }
     a.mu63 = (u32)((((u128)1) << 63) / q);
     a.mu64 = (u32)((((u128)1) << 64) / q);
     return a;

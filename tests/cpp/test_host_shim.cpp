@@ -20,7 +20,7 @@ using namespace seal_b200;
     do {                                                                     \
         if (!(cond)) {                                                       \
             std::fprintf(stderr, "FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond); \
-            return 1;                                                        \
+            std::_Exit(1); /* std::cout is redirected into a local: no unwinding */ \
         }                                                                    \
     } while (0)
 
@@ -75,6 +75,20 @@ static void dct_by_ops(std::vector<Ciphertext> &data, Evaluator &ev, FractionalE
     }
 }
 
+// Independent deep copies of a block that are NOT one contiguous allocation: the device allocator
+// is a stream-ordered pool, which may well hand consecutive requests adjacent addresses, so a live
+// spacer ciphertext is allocated between consecutive copies.
+static std::vector<Ciphertext> scattered_copies(const std::vector<Ciphertext> &block, std::vector<Ciphertext> &spacers)
+{
+    std::vector<Ciphertext> out;
+    out.reserve(block.size());
+    for (size_t i = 0; i < block.size(); ++i) {
+        out.emplace_back(block[i]);
+        spacers.emplace_back(block[i]);
+    }
+    return out;
+}
+
 static std::vector<uint64_t> fetch(const std::vector<Ciphertext> &v)
 {
     const size_t w = v[0].context()->ct_words(2);
@@ -104,7 +118,8 @@ int main(int argc, char **argv)
     const std::vector<uint64_t> input = fetch(block);
 
     // (1) op by op, on independent copies (what the reference does)
-    std::vector<Ciphertext> by_ops(block.begin(), block.end());
+    std::vector<Ciphertext> spacers;
+    std::vector<Ciphertext> by_ops = scattered_copies(block, spacers);
     REQUIRE(!is_contiguous(by_ops));
     dct_by_ops(by_ops, evaluator, encoder);
     const std::vector<uint64_t> dct_ops = fetch(by_ops);
@@ -113,7 +128,8 @@ int main(int argc, char **argv)
     REQUIRE(fetch(block) == input);  // copies are independent
 
     // (2) fused encrypted_dct on scattered copies, then quantize_fhe op by op
-    std::vector<Ciphertext> scattered(block.begin(), block.end());
+    std::vector<Ciphertext> scattered = scattered_copies(block, spacers);
+    REQUIRE(!is_contiguous(scattered));
     encrypted_dct(scattered, evaluator, encoder, encryptor);
     REQUIRE(fetch(scattered) == dct_ops);
     quantize_fhe(scattered, quant, evaluator, encoder, encryptor);
