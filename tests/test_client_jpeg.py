@@ -1,0 +1,171 @@
+"""Client-side tail of the JPEG pipeline: host/jpeg_entropy_b200.hpp and the
+client_jpeg_pack_b200 tool -- the restatement of client_jpeg --recieve after decryption
+(homo/client_jpeg.cpp:221-291, homo/fhe_image.h:331-397, 508-521).  CPU only.  The independent
+checker is PIL's JPEG decoder: the files must decode, and decode to the image the coefficients came
+from."""
+import io
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import PKG_NAME, ROOT
+
+SRC = os.path.join(ROOT, PKG_NAME, "client", "client_jpeg_pack_b200.cpp")
+HDR = os.path.join(ROOT, PKG_NAME, "host", "jpeg_entropy_b200.hpp")
+EXE = os.path.join(ROOT, PKG_NAME, "client", "client_jpeg_pack_b200")
+# fhe_image.h:34
+S_ZIGZAG = [0, 1, 5, 6, 14, 15, 27, 28, 2, 4, 7, 13, 16, 26, 29, 42, 3, 8, 12, 17, 25, 30, 41, 43, 9, 11, 18, 24, 31, 40, 44,
+            53, 10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48,
+            49, 57, 58, 62, 63]
+
+
+def build_pack():
+    if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in (SRC, HDR)):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-o", EXE, SRC])
+    return EXE
+
+
+def synthetic_image(width, height, seed=3):
+    """Smooth gradients plus a little noise and one sharp edge: every coefficient class shows up."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:height, 0:width]
+    img = np.stack([128 + 100 * np.sin(x / 7.0) * np.cos(y / 9.0), 40 + 5.0 * x + 2.0 * y, 255.0 * ((x // 5 + y // 6) % 2)], axis=-1)
+    img += rng.normal(0, 2.0, img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def plaintext_pipeline(image, quant_y=None, quant_c=None):
+    """client --send order + the server's arithmetic in the clear: per 8x8 tile R,G,B -> Y,Cb,Cr
+    (fhe_image.h:317-319), 2-D DCT (dct(), :400-484, equal to the orthonormal DCT-II), optional
+    division by the quantisation tables (:294-305).  Returns [tile][3][64] doubles, natural order."""
+    from scipy.fft import dctn
+    h, w, _ = image.shape
+    out = []
+    for by in range(h // 8):
+        for bx in range(w // 8):
+            blk = image[8 * by:8 * by + 8, 8 * bx:8 * bx + 8].astype(float)
+            r, g, b = blk[..., 0], blk[..., 1], blk[..., 2]
+            chans = [0.299 * r + 0.587 * g + 0.114 * b - 128.0, -0.168736 * r - 0.331264 * g + 0.5 * b,
+                     0.5 * r - 0.418688 * g - 0.081312 * b]
+            tile = []
+            for c, ch in enumerate(chans):
+                d = dctn(ch, type=2, norm="ortho").reshape(64)
+                qt = quant_y if c == 0 else quant_c
+                tile.append(d / np.asarray(qt, dtype=float) if qt is not None else d)
+            out.append(tile)
+    return np.asarray(out)
+
+
+def pack(values, width, height, quality, path):
+    raw = path + ".f64"
+    np.asarray(values, dtype="<f8").tofile(raw)
+    subprocess.check_call([build_pack(), "pack", str(width), str(height), str(quality), raw, path])
+    return path
+
+
+def decode_rgb(path):
+    from PIL import Image
+    with Image.open(path) as im:
+        im.load()
+        assert im.format == "JPEG" and im.mode == "RGB"
+        return np.asarray(im.convert("RGB"))
+
+
+def segments(data: bytes):
+    """marker -> list of payloads, up to SOS"""
+    out, i = {}, 2
+    assert data[:2] == b"\xff\xd8"
+    while i < len(data):
+        assert data[i] == 0xFF
+        marker, ln = data[i + 1], int.from_bytes(data[i + 2:i + 4], "big")
+        out.setdefault(marker, []).append(data[i + 4:i + 2 + ln])
+        i += 2 + ln
+        if marker == 0xDA:
+            break
+    return out
+
+
+def dht_tables(payloads):
+    tabs = {}
+    for p in payloads:
+        i = 0
+        while i < len(p):
+            ident, bits = p[i], list(p[i + 1:i + 17])
+            n = sum(bits)
+            tabs[ident] = (bits, list(p[i + 17:i + 17 + n]))
+            i += 17 + n
+    return tabs
+
+
+def test_tables_are_the_standard_ones(tmp_path, pkg):
+    from PIL import Image
+    img = synthetic_image(16, 16)
+    ours = open(pack(plaintext_pipeline(img), 16, 16, 0, str(tmp_path / "a.jpg")), "rb").read()
+    buf = io.BytesIO()
+    Image.fromarray(img).save(buf, "JPEG", quality=90, optimize=False, subsampling=0)
+    theirs = segments(buf.getvalue())
+    mine = segments(ours)
+    # Annex K.3 tables: identical to the ones PIL / libjpeg emit when not optimising
+    assert dht_tables(mine[0xC4]) == dht_tables(theirs[0xC4])
+    # QUALITY = 0 (fhe_image.h:32) -> header tables of ones (client_jpeg.cpp:224-228), 8-bit precision
+    dqt = mine[0xDB][0]
+    assert dqt[0] == 0 and set(dqt[1:65]) == {1} and dqt[65] == 1 and set(dqt[66:130]) == {1}
+    # quality 100 -> the divisors the server applies, in zig-zag order
+    q100 = segments(open(pack(plaintext_pipeline(img, pkg.YQT, pkg.UVQT), 16, 16, 100, str(tmp_path / "b.jpg")), "rb").read())[0xDB][0]
+    want_y, want_c = [0] * 64, [0] * 64
+    for i in range(64):
+        want_y[S_ZIGZAG[i]], want_c[S_ZIGZAG[i]] = pkg.YQT[i], pkg.UVQT[i]
+    assert list(q100[1:65]) == want_y and list(q100[66:130]) == want_c
+    # SOF0: baseline, 16x16, three components without subsampling
+    assert mine[0xC0][0] == bytes([8, 0, 16, 0, 16, 3, 1, 0x11, 0, 2, 0x11, 1, 3, 0x11, 1])
+
+
+@pytest.mark.parametrize("width,height", [(8, 8), (48, 24)])
+def test_unquantised_stream_decodes_to_the_image(tmp_path, width, height):
+    """What the reference's server actually sends back (DCT without quantize_fhe) with the
+    reference's QUALITY = 0 header: a near-lossless JPEG."""
+    img = synthetic_image(width, height)
+    got = decode_rgb(pack(plaintext_pipeline(img), width, height, 0, str(tmp_path / "u.jpg")))
+    assert got.shape == img.shape
+    rms = float(np.sqrt(np.mean((got.astype(float) - img.astype(float)) ** 2)))
+    assert rms < 1.5, rms
+
+
+def test_quantised_stream_matches_a_standard_encoder(tmp_path, pkg):
+    """With quantize_fhe applied (YQT / UVQT) and quality 100 in the header, the decoded picture is
+    what any baseline encoder with those tables produces."""
+    import cv2
+    width, height = 64, 40
+    img = synthetic_image(width, height, seed=9)
+    ours = decode_rgb(pack(plaintext_pipeline(img, pkg.YQT, pkg.UVQT), width, height, 100, str(tmp_path / "q.jpg")))
+    # libjpeg through OpenCV at quality 50 = exactly the Annex K tables YQT / UVQT, 4:4:4
+    ok, enc = cv2.imencode(".jpg", img[..., ::-1], [cv2.IMWRITE_JPEG_QUALITY, 50, cv2.IMWRITE_JPEG_SAMPLING_FACTOR,
+                                                      cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444])
+    assert ok
+    seg = segments(enc.tobytes())
+    tabs = b"".join(seg[0xDB])
+    assert list(tabs[1:65]) == [pkg.YQT[S_ZIGZAG.index(p)] for p in range(64)]
+    theirs = cv2.imdecode(enc, cv2.IMREAD_COLOR)[..., ::-1]
+    rms_pair = float(np.sqrt(np.mean((ours.astype(float) - theirs.astype(float)) ** 2)))
+    rms_orig = float(np.sqrt(np.mean((ours.astype(float) - img.astype(float)) ** 2)))
+    rms_ref = float(np.sqrt(np.mean((theirs.astype(float) - img.astype(float)) ** 2)))
+    # same loss against the original as libjpeg (17.23 vs 17.20 on this picture), and the two decodes
+    # differ by far less than that loss (integer vs floating colour conversion and DCT)
+    assert abs(rms_orig - rms_ref) < 0.25, (rms_orig, rms_ref)
+    assert rms_pair < 0.25 * rms_ref, (rms_pair, rms_ref)
+
+
+def test_rms_tool_and_rounding(tmp_path):
+    a = np.arange(48, dtype=np.uint8)
+    b = a.copy()
+    b[::2] += 2
+    a.tofile(tmp_path / "a.rgb")
+    b.tofile(tmp_path / "b.rgb")
+    out = subprocess.run([build_pack(), "rms", str(tmp_path / "a.rgb"), str(tmp_path / "b.rgb")], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("RMSError,") and out.stdout.rstrip().endswith(",")
+    assert abs(float(out.stdout.split(",")[1]) - np.sqrt(2.0)) < 1e-5
+    # bad sizes are refused
+    r = subprocess.run([build_pack(), "pack", "16", "16", "0", str(tmp_path / "a.rgb"), str(tmp_path / "x.jpg")], capture_output=True)
+    assert r.returncode == 2

@@ -135,3 +135,11 @@ def test_server_jpeg_end_to_end_on_gpu(pkg, oracle_mod, tmp_path):
             for p in (0, 1, 9, 63):
                 val = o.decode(o.decrypt(sk, got[(t * 3 + c) * 64 + p], 2))
                 assert abs(val - plain[c][p]) < 1e-3, (t, c, p, val, plain[c][p])
+    # client_jpeg --recieve (client_jpeg.cpp:255-291): decrypt + decode every ciphertext of the
+    # stream, round, entropy-code with QUALITY = 0 header tables; the file must decode (PIL) to the
+    # picture that was encrypted
+    from test_client_jpeg import decode_rgb, pack
+    values = np.array([o.decode(o.decrypt(sk, ct, 2)) for ct in got]).reshape(len(tiles), 3, 64)
+    rgb = decode_rgb(pack(values, width, height, 0, str(tmp_path / "fhe.jpg")))
+    rms = float(np.sqrt(np.mean((rgb.astype(float) - image.astype(float)) ** 2)))
+    assert rms < 1.5, rms
