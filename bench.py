@@ -87,9 +87,11 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_sample(threads, blocks, min_seconds=0.0):
+def cpu_sample(threads, blocks, min_seconds=0.0, keep_first=None):
     """Oracle (CPU restatement of the reference's op-by-op graph) on a bounded sample: `blocks`
-    blocks per pass, repeated on fresh inputs until `min_seconds` of CPU work were timed."""
+    blocks per pass, repeated on fresh inputs until `min_seconds` of CPU work were timed.
+    keep_first: a list that receives the oracle's OUTPUT of the first pass (blocks 0 .. blocks-1 of
+    the workload), so the caller can check the GPU's output of the same blocks against it."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py
     pkg = importlib.import_module("fully-homomorphic-image-processing_b200")
@@ -98,6 +100,8 @@ def cpu_sample(threads, blocks, min_seconds=0.0):
     while True:
         data = o.fill_uniform(64 * done, 64 * blocks)
         secs += o.bench_dct_quant(data, blocks, pkg.YQT, threads)
+        if keep_first is not None and done == 0:
+            keep_first.append(data)
         done += blocks
         if secs >= min_seconds:
             break
@@ -218,6 +222,15 @@ def main():
     ms = float(tmax.item())
     value = world * B * args.steps / (ms * 1e-3)
 
+    # rank 0 keeps its first SPOT output blocks (blocks 0..SPOT-1 of the workload) for the bit-exact
+    # check against the oracle in the cpu_baseline leg
+    SPOT = min(4, B)
+    spot = None
+    if rank == 0 and not args.no_cpu:
+        import numpy as np
+        spot = np.empty(SPOT * ctx.block_words(), dtype=np.uint64)
+        ctx.download(spot, d_out.data_ptr())
+
     # edge collective only: checksum of every rank's output
     cs = ctx.checksum(d_out.data_ptr(), words)
     cs_t = torch.tensor([cs & 0x7FFFFFFFFFFFFFFF], dtype=torch.int64, device="cuda")
@@ -297,11 +310,17 @@ def main():
                 "path_achieved": value / world * 2 * 64 * ct_bytes / 1e9,
                 "path_frac": value / world * 2 * 64 * ct_bytes / 1e9 / peak}
 
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and not args.no_cpu:
         threads = os.cpu_count() or 1
-        v, secs, done = cpu_sample(threads, 8 * threads, min_seconds=12.0)
+        first = []
+        v, secs, done = cpu_sample(threads, 8 * threads, min_seconds=12.0, keep_first=first)
         v1, _, _ = cpu_sample(1, 4)
+        # the oracle as the checker: the blocks it just computed are blocks 0.. of rank 0's chunk
+        nchk = min(SPOT, 8 * threads)
+        if not (first[0][: nchk * ctx.block_words()] == spot[: nchk * ctx.block_words()]).all():
+            raise SystemExit("bench.py: GPU output differs from the oracle on the spot-checked blocks")
+        parity = {"blocks": nchk, "bit_exact": True, "against": "oracle, blocks 0.. of rank 0's timed chunk"}
         cpu = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{done} blocks of the same workload in {secs:.1f} s on {threads} threads "
                          f"(oracle, op-by-op reference graph); single thread: {v1:.2f} blocks/s",
@@ -320,7 +339,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ebytes, "d2h_bytes_per_step": ebytes,
                     "blocks_per_step": EB, "steps": e2e_steps},
             "roofline": roofline, "cpu_baseline": cpu, "server_jpeg_tile": tile_info,
-            "output_checksum_xor": hex(int(cs_t.item())),
+            "output_checksum_xor": hex(int(cs_t.item())), "parity_spot_check": parity,
         }))
     plan.close()
     ctx.close()

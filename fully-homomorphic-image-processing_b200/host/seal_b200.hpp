@@ -402,6 +402,7 @@ public:
         Ciphertext dest(*ctx_, a.size() + b.size() - 1);
         check(fhe_multiply(ctx_->handle(), a.device_data(), a.size(), b.device_data(), b.size(), dest.device_data(), 1));
         a = std::move(dest);
+        if (auto_relin_) relinearize(a, *auto_relin_);
     }
     // Evaluator::square(a) (fhe_resize.h:174; fhe_decode.h:67 ...)
     void square(Ciphertext &a)
@@ -410,7 +411,17 @@ public:
         Ciphertext dest(*ctx_, 2 * a.size() - 1);
         check(fhe_square(ctx_->handle(), a.device_data(), a.size(), dest.device_data(), 1));
         a = std::move(dest);
+        if (auto_relin_) relinearize(a, *auto_relin_);
     }
+    // Relinearisation policy (an EXTENSION: homo/ never relinearises, so its ciphertexts grow to
+    // size 6 in the resize graphs and 22 in the decode graphs).  With keys set, every ct x ct
+    // product (multiply, square; single and batched) is brought back to size 2 immediately -- the
+    // insertion point BASELINE config 5 ("deep-multiply + relinearize") asks for -- so the op
+    // libraries of fhe_resize_b200.hpp / fhe_decode_b200.hpp run unchanged on size-2 operands.
+    // The keys need evk.size() >= 1 (only size 3 -> 2 occurs).  nullptr restores the reference's
+    // behaviour.  Results decrypt to the same plaintext but are different ciphertexts.
+    void set_relinearization(const EvaluationKeys *evk) { auto_relin_ = evk; }
+    const EvaluationKeys *relinearization() const { return auto_relin_; }
     // Evaluator::relinearize(a, evk): back to size 2 (north_star; no call site in homo/)
     void relinearize(Ciphertext &a, const EvaluationKeys &evk)
     {
@@ -452,6 +463,7 @@ public:
         CiphertextBatch dest(*ctx_, a.count(), a.size() + b.size() - 1);
         check(fhe_multiply(ctx_->handle(), a.device_data(), a.size(), b.device_data(), b.size(), dest.device_data(), a.count()));
         a = std::move(dest);
+        if (auto_relin_) relinearize(a, *auto_relin_);
     }
     void square(CiphertextBatch &a)
     {
@@ -459,6 +471,7 @@ public:
         CiphertextBatch dest(*ctx_, a.count(), 2 * a.size() - 1);
         check(fhe_square(ctx_->handle(), a.device_data(), a.size(), dest.device_data(), a.count()));
         a = std::move(dest);
+        if (auto_relin_) relinearize(a, *auto_relin_);
     }
     void relinearize(CiphertextBatch &a, const EvaluationKeys &evk)
     {
@@ -528,6 +541,7 @@ private:
         return t;
     }
     const Context *ctx_;
+    const EvaluationKeys *auto_relin_ = nullptr;
     std::unordered_map<std::string, fhe_ptab *> cache_;
     std::unordered_map<std::string, std::shared_ptr<void>> plans_;
 };

@@ -176,6 +176,39 @@ int main(int argc, char **argv)
             threw = true;
         }
         REQUIRE(threw);
+        // relinearisation policy (Evaluator::set_relinearization, an extension): every product is
+        // brought back to size 2; argv[4] = evaluation keys (coefficient form), argv[5] = dbc
+        if (argc > 5) {
+            std::ifstream kin(argv[4], std::ios::binary);
+            REQUIRE((bool)kin);
+            kin.seekg(0, std::ios::end);
+            std::vector<uint64_t> kw((size_t)kin.tellg() / 8);
+            kin.seekg(0);
+            kin.read((char *)kw.data(), (std::streamsize)(kw.size() * 8));
+            const uint32_t dbc = (uint32_t)std::atoi(argv[5]);
+            EvaluationKeys evk(ctx, kw.data(), dbc, 1);
+            evaluator.set_relinearization(&evk);
+            Ciphertext s2, lin2, Ar = ct_at(0), Br = ct_at(1), tr = ct_at(4);
+            next_zero = 8;
+            homomorphic_sin(Ar, s2, evaluator, encoder, zeros);
+            REQUIRE(s2.size() == 2);
+            dump(s2);
+            Linear(lin2, Ar, Br, tr, evaluator, encoder, zeros);
+            REQUIRE(lin2.size() == 2);
+            dump(lin2);
+            // batched == single under the same policy
+            CiphertextBatch xs(ctx, 2, 2), rs;
+            xs.set(0, ct_at(0));
+            xs.set(1, ct_at(1));
+            next_zero = 8;
+            homomorphic_sin(xs, rs, evaluator, encoder, zeros);
+            REQUIRE(rs.size() == 2 && same(rs.get(0), s2));
+            evaluator.set_relinearization(nullptr);
+            Ciphertext s3, Ar2 = ct_at(0);
+            next_zero = 8;
+            homomorphic_sin(Ar2, s3, evaluator, encoder, zeros);
+            REQUIRE(s3.size() == 11);
+        }
         std::printf("PASS\n");
         return 0;
     } catch (const std::exception &e) {

@@ -72,6 +72,46 @@ def resize_bicubic_oracle(o, src, ow, oh, dw, dh, fracs):
     return np.concatenate(out), nf
 
 
+def sin_relin_oracle(o, x, zero, evk, dbc):
+    """homomorphic_sin (fhe_decode.h:48-120) op by op on the oracle with every ct x ct product
+    relinearised to size 2 (host/seal_b200.hpp Evaluator::set_relinearization)."""
+    import math
+
+    def rl(c):
+        return o.relinearize(c, 3, evk, dbc, 1)
+
+    def sq(c):
+        return rl(o.square(c, 2))
+
+    def mul(a, b):
+        return rl(o.multiply(a, 2, b, 2))
+
+    sh = x.copy()
+    o.add_plain(sh, o.encode(-3 * math.pi / 2.0))
+    p2 = sq(sh)
+    p4 = sq(sq(sh))
+    p6 = mul(mul(sq(sq(sh)), sh), sh)
+    p8 = sq(sq(sq(sh)))
+    p10 = mul(mul(sq(sq(sq(sh))), sh), sh)
+    res = zero.copy()
+    o.add_plain(res, o.encode(-1.0))
+    for term, coef in ((p2, 0.5), (p4, -1 / 24.0), (p6, 1 / 720.0), (p8, -1 / 40320.0), (p10, 1 / 3628800.0)):
+        o.multiply_plain(term, o.encode(coef))
+        o.add(res, term)
+    return res
+
+
+def linear_relin_oracle(o, A, B, t, evk, dbc):
+    """Linear (fhe_resize.h:191-204): (1 - t) A + t B via negate, add_plain(1.0), two multiplies, add."""
+    one_minus_t = t.copy()
+    o.negate(one_minus_t)
+    o.add_plain(one_minus_t, o.encode(1.0))
+    a = o.relinearize(o.multiply(one_minus_t, 2, A.copy(), 2), 3, evk, dbc, 1)
+    b = o.relinearize(o.multiply(B.copy(), 2, t.copy(), 2), 3, evk, dbc, 1)
+    o.add(a, b)
+    return a
+
+
 @pytest.mark.gpu
 def test_resize_decode_host_layer_matches_oracle_on_gpu(pkg, oracle_mod, tmp_path):
     exe = build_exe(pkg)
@@ -86,9 +126,12 @@ def test_resize_decode_host_layer_matches_oracle_on_gpu(pkg, oracle_mod, tmp_pat
     for i, v in enumerate(vals):
         data[i * W:(i + 1) * W] = o.encrypt(pk, o.encode(v), 100 + i)
     data[4 * W:5 * W] = o.encrypt(pk, o.encode(0.625), 200)
-    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    fin, fout, fkey = str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(tmp_path / "evk.bin")
     data.tofile(fin)
-    r = subprocess.run([exe, str(n), fin, fout], capture_output=True, text=True, timeout=900)
+    dbc = 16
+    evk = o.evk_gen(sk, dbc, 1, 77)
+    evk.tofile(fkey)
+    r = subprocess.run([exe, str(n), fin, fout, fkey, str(dbc)], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("PASS")
     got = np.fromfile(fout, dtype=np.uint64)
@@ -117,9 +160,15 @@ def test_resize_decode_host_layer_matches_oracle_on_gpu(pkg, oracle_mod, tmp_pat
     tz = np.zeros(W, dtype=np.uint64)
     o.add_plain(tz, o.encode(0.375))
     want.append(tz)
+    # Evaluator::set_relinearization: the same graphs with every product relinearised (dbc 16)
+    s_rl = sin_relin_oracle(o, ct(0), ct(8), evk, dbc)
+    lin_rl = linear_relin_oracle(o, ct(0), ct(1), ct(4), evk, dbc)
+    want += [s_rl, lin_rl]
     want = np.concatenate(want)
     assert got.size == want.size
     assert (got == want).all()
+    # one multiplicative level fits the single 54-bit prime: (1 - t) A + t B = 0.375 * 12 + 0.625 * 200
+    assert abs(o.decode(o.decrypt(sk, lin_rl, 2)) - 129.5) < 1e-6
     # (what the Cubic decrypts to is checked in tests/test_oracle_behz.py with a two-prime modulus;
     # coeff_modulus_128(2048) is one 54-bit prime, too small for two multiplicative levels)
     assert abs(o.decode(o.decrypt(sk, tz, 2)) - 0.375) < 1e-9

@@ -3,10 +3,14 @@
 // approximated_step_batched (host/fhe_decode_b200.hpp) on synthetic uniform ciphertexts, transparent
 // server-side encryptions.  One run-length pair expands to width*height ciphertexts of size 22 through
 // 2 * positions * degree Taylor series (15 ciphertext products each, sizes up to 11).
-// Not the headline bench (bench.py).  Usage: bench_decode [n] [positions] [degree] [order] -> JSON line
+// With a 5th argument dbc > 0 every ct x ct product is relinearised (Evaluator::set_relinearization,
+// "deep-multiply + relinearize" of config 5) with synthetic evaluation keys: all operands stay size 2.
+// Not the headline bench (bench.py).  Usage: bench_decode [n] [positions] [degree] [order] [dbc] -> JSON line
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
+#include <vector>
 
 #include "../fully-homomorphic-image-processing_b200/host/fhe_decode_b200.hpp"
 
@@ -18,8 +22,19 @@ int main(int argc, char **argv)
         const uint32_t n = argc > 1 ? (uint32_t)std::atoi(argv[1]) : 8192;
         const int npos = argc > 2 ? std::atoi(argv[2]) : 64, degree = argc > 3 ? std::atoi(argv[3]) : 12;
         const int order = argc > 4 ? std::atoi(argv[4]) : 64;
+        const uint32_t dbc = argc > 5 ? (uint32_t)std::atoi(argv[5]) : 0;
         Context ctx(n);
         Evaluator evaluator(ctx);
+        std::unique_ptr<EvaluationKeys> evk;
+        if (dbc) {
+            // timing only: any residues below every q_j serve as keys
+            const uint32_t k = ctx.coeff_mod_count(), digits = fhe_evk_digits(ctx.handle(), dbc);
+            std::vector<uint64_t> kw((size_t)k * digits * 2 * k * n);
+            uint64_t z = 0x5EED;
+            for (auto &w : kw) { z = z * 6364136223846793005ull + 1442695040888963407ull; w = z >> 12; }
+            evk.reset(new EvaluationKeys(ctx, kw.data(), dbc, 1));
+            evaluator.set_relinearization(evk.get());
+        }
         FractionalEncoder encoder(ctx, 100, 100);
         Encryptor encryptor(ctx);
         Ciphertext amplitude(ctx, 2), index(ctx, 2), count(ctx, 2);
@@ -43,10 +58,10 @@ int main(int argc, char **argv)
         }
         const double series = 2.0 * npos * degree, products = series * 15 + (double)npos * degree + npos;
         std::printf("{\"what\": \"approximated_step_batched (homomorphic RLE step, fhe_decode.h:202-242), n=%u k=%u, "
-                    "%d positions, degree %d, order %d, synthetic ciphertexts, transparent server-side encryptions\", "
+                    "%d positions, degree %d, order %d, synthetic ciphertexts, transparent server-side encryptions, relinearisation dbc %u (0 = none, as the reference)\", "
                     "\"seconds_per_run_length_pair\": %.4f, \"taylor_series_per_s\": %.1f, \"ct_products_per_s\": %.1f, "
                     "\"out_ct_size\": %zu, \"kernel_launches\": %llu}\n",
-                    n, ctx.coeff_mod_count(), npos, degree, order, best, series / best, products / best, out_size, launches);
+                    n, ctx.coeff_mod_count(), npos, degree, order, dbc, best, series / best, products / best, out_size, launches);
         return 0;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "exception: %s\n", e.what());
