@@ -309,6 +309,15 @@ def main():
                 "stage_ms": dict(zip(names, stage)),
                 "path_achieved": value / world * 2 * 64 * ct_bytes / 1e9,
                 "path_frac": value / world * 2 * 64 * ct_bytes / 1e9 / peak}
+    # what actually bounds the path: constant multiplications `mulc` on the FMA-heavy
+    # pipe.  Per block: 2 transforms x 256 limb-polynomials x n/2 log2 n butterflies + 256 per
+    # (poly, limb, position) in the pointwise network; peak = tools/ubench (profiles/r01d_ubench.txt).
+    logn = N_RING.bit_length() - 1
+    mulc_per_block = 2 * 64 * 2 * ctx.k * (N_RING // 2) * logn + 256 * 2 * ctx.k * N_RING
+    roofline["int_multiply_pipe"] = {"achieved": value / world * mulc_per_block / 1e9, "peak": 1227.2,
+                                     "unit": "G mulc/s per GPU", "frac": value / world * mulc_per_block / 1e9 / 1227.2,
+                                     "mulc_per_block": mulc_per_block,
+                                     "peak_source": "measured, tools/ubench at 1965 MHz (profiles/r01d_ubench.txt)"}
 
     cpu, parity = None, None
     if rank == 0 and not args.no_cpu:
