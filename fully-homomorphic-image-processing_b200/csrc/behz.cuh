@@ -205,15 +205,16 @@ __global__ void __launch_bounds__(256) k_behz_tensor(const u64 *__restrict__ A, 
                                                       const u64 *__restrict__ mod, const u64 *__restrict__ r0,
                                                       const u64 *__restrict__ r1)
 {
+    // grid = (nl * n / 256, ciphertexts (strided)): r = limb * n + pos without a 64-bit division
     const uint32_t sd = s1 + s2 - 1;
-    const unsigned long long per_ct = (unsigned long long)nl << logn, total = n_ct * per_ct;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long ct = i / per_ct, r = i % per_ct;  // r = limb * n + pos
-        const uint32_t j = (uint32_t)(r >> logn);
+    const unsigned long long per_ct = (unsigned long long)nl << logn;
+    const unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t j = (uint32_t)(r >> logn);
+    const u64 m = mod[j], m0 = r0[j], m1 = r1[j];
+    for (unsigned long long ct = blockIdx.y; ct < n_ct; ct += gridDim.y) {
         const u64 *a = A + ct * s1 * per_ct + r, *b = Bm + ct * s2 * per_ct + r;
         u64 *d = D + ct * sd * per_ct + r;
-        behz_tensor_elem(a, b, d, per_ct, s1, s2, mod[j], r0[j], r1[j]);
+        behz_tensor_elem(a, b, d, per_ct, s1, s2, m, m0, m1);
     }
 }
 
