@@ -196,6 +196,10 @@ int main(int argc, char **argv)
             Linear(lin2, Ar, Br, tr, evaluator, encoder, zeros);
             REQUIRE(lin2.size() == 2);
             dump(lin2);
+            Ciphertext cub2, Cr = ct_at(2), Dr = ct_at(3);
+            Cubic(cub2, Ar, Br, Cr, Dr, tr, evaluator, encoder, zeros);
+            REQUIRE(cub2.size() == 2);
+            dump(cub2);
             // batched == single under the same policy
             CiphertextBatch xs(ctx, 2, 2), rs;
             xs.set(0, ct_at(0));

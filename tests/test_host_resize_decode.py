@@ -101,6 +101,38 @@ def sin_relin_oracle(o, x, zero, evk, dbc):
     return res
 
 
+def cubic_relin_oracle(o, A, B, C, D, t, evk, dbc):
+    """Cubic (fhe_resize.h:143-189, incl. t3 = t * t) with every product relinearised."""
+    def rl(c):
+        return o.relinearize(c, 3, evk, dbc, 1)
+
+    def mp(x, v):
+        y = x.copy()
+        o.multiply_plain(y, o.encode(float(v)))
+        return y
+
+    a = mp(B, 3)
+    o.sub(a, A)
+    o.sub(a, mp(C, 3))
+    o.add(a, D)
+    b = mp(A, 2)
+    o.sub(b, mp(B, 5))
+    o.add(b, mp(C, 4))
+    o.sub(b, D)
+    c = C.copy()
+    o.sub(c, A)
+    t2 = rl(o.square(t.copy(), 2))
+    t3 = rl(o.multiply(t.copy(), 2, t.copy(), 2))
+    a = rl(o.multiply(a, 2, t3, 2))
+    b = rl(o.multiply(b, 2, t2, 2))
+    c = rl(o.multiply(c, 2, t.copy(), 2))
+    o.add(a, b)
+    o.add(a, c)
+    o.multiply_plain(a, o.encode(0.5))
+    o.add(a, B)
+    return a
+
+
 def linear_relin_oracle(o, A, B, t, evk, dbc):
     """Linear (fhe_resize.h:191-204): (1 - t) A + t B via negate, add_plain(1.0), two multiplies, add."""
     one_minus_t = t.copy()
@@ -163,7 +195,8 @@ def test_resize_decode_host_layer_matches_oracle_on_gpu(pkg, oracle_mod, tmp_pat
     # Evaluator::set_relinearization: the same graphs with every product relinearised (dbc 16)
     s_rl = sin_relin_oracle(o, ct(0), ct(8), evk, dbc)
     lin_rl = linear_relin_oracle(o, ct(0), ct(1), ct(4), evk, dbc)
-    want += [s_rl, lin_rl]
+    cub_rl = cubic_relin_oracle(o, ct(0), ct(1), ct(2), ct(3), ct(4), evk, dbc)
+    want += [s_rl, lin_rl, cub_rl]
     want = np.concatenate(want)
     assert got.size == want.size
     assert (got == want).all()
