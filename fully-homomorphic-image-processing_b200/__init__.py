@@ -108,6 +108,7 @@ def lib():
         "fhe_jpeg_plan_destroy": (None, [vp]),
         "fhe_jpeg_rgb_tiles": (i32, [vp, vp, vp, vp, u64]),
         "fhe_device_zero": (i32, [vp, vp, C.c_size_t]),
+        "fhe_encrypt_transparent": (i32, [vp, u64p, u32, vp]),
         "fhe_multiply": (i32, [vp, vp, u32, vp, u32, vp, u64]),
         "fhe_square": (i32, [vp, vp, u32, vp, u64]),
         "fhe_evk_digits": (u32, [vp, u32]),
@@ -130,7 +131,7 @@ EXPORTED_SYMBOLS = (
     "fhe_ntt_forward", "fhe_ntt_inverse", "fhe_dct_plan_create", "fhe_dct_plan_destroy",
     "fhe_dct8x8_quantize", "fhe_dct8x8_quantize_host", "fhe_fill_uniform", "fhe_checksum",
     "fhe_launch_count", "fhe_set_dct_chunk_blocks", "fhe_set_stage_timing", "fhe_get_stage_times",
-    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_multiply", "fhe_square", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
+    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_encrypt_transparent", "fhe_multiply", "fhe_square", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
 )
 
 
@@ -241,6 +242,12 @@ class Context:
 
     def ntt_forward(self, a, n_limbpolys): _check(lib().fhe_ntt_forward(self.h, C.c_void_p(a), n_limbpolys))
     def ntt_inverse(self, a, n_limbpolys): _check(lib().fhe_ntt_inverse(self.h, C.c_void_p(a), n_limbpolys))
+
+    def encrypt_transparent(self, plains, dptr):
+        """(Delta * m, 0) for every row of `plains` ([count][n], coefficients < t) into dptr."""
+        import numpy as np
+        arr = np.ascontiguousarray(plains, dtype=np.uint64).reshape(-1, self.n)
+        _check(lib().fhe_encrypt_transparent(self.h, _np_ptr(arr), arr.shape[0], C.c_void_p(dptr)))
 
     # ---- synthetic inputs / checks
     def fill_uniform(self, dptr, first_ct, n_ct, size=2, seed=0x5EA1B200):

@@ -374,6 +374,12 @@ struct fhe_ctx {
     // optional per-kernel timing of the DCT path
     bool stage_timing = false;
     std::vector<cudaEvent_t> stage_ev;  // 4 per chunk of the last call
+    // pinned ring for small host -> device parameter uploads that must not synchronise the stream
+    // (fhe_encrypt_transparent): kRing slots of n words, one event per slot
+    static constexpr int kRing = 32;
+    u64 *h_ring = nullptr;
+    cudaEvent_t ev_ring[kRing]{};
+    uint64_t ring_next = 0;
     // Evaluator::multiply / square / relinearize state, built on first use (behz_api.inc)
     struct BehzState *behz = nullptr;
 };
@@ -595,6 +601,10 @@ void fhe_ctx_destroy(fhe_ctx *c)
     clear_stage_events(c);
     behz_state_destroy(c->behz);
     cudaFree(c->d_tw); cudaFree(c->d_itw); cudaFree(c->d_scratch);
+    if (c->h_ring) {
+        cudaFreeHost(c->h_ring);
+        for (int i = 0; i < fhe_ctx::kRing; ++i) cudaEventDestroy(c->ev_ring[i]);
+    }
     if (c->s_in) cudaStreamDestroy(c->s_in);
     if (c->s_out) cudaStreamDestroy(c->s_out);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -791,6 +801,62 @@ static int build_plain_tables(fhe_ctx *c, const uint64_t *plain, uint32_t count,
     cudaFree(d_plain);
     cudaFree(d_lift);
     return rc;
+}
+
+// dst[pl][0][j][c] = Delta-scaled plaintext (as k_plain_scale), dst[pl][1] = 0
+__global__ void k_encrypt_transparent(const u64 *plain, u64 *dst, unsigned long long total, RingDev R)
+{
+    // total = count * 2 * k * n; i = ((pl * 2 + poly) * k + j) * n + c
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i & (R.n - 1));
+        const unsigned long long lp = i >> R.logn;            // (pl * 2 + poly) * k + j
+        const uint32_t j = (uint32_t)(lp % R.k);
+        const unsigned long long pp = lp / R.k;               // pl * 2 + poly
+        if (pp & 1) { dst[i] = 0; continue; }
+        const u64 m = plain[(pp >> 1) * R.n + c];
+        u64 lo = R.delta[j] * m, hi = mulhi_u64(R.delta[j], m);
+        if (m >= R.plain_thr) {
+            u64 s = lo + R.q_mod_t;
+            hi += (s < lo);
+            lo = s;
+        }
+        dst[i] = barrett128(lo, hi, R.limb[j].a.q, R.ratio0[j], R.ratio1[j]);
+    }
+}
+
+int fhe_encrypt_transparent(fhe_ctx *c, const uint64_t *plain, uint32_t count, uint64_t *d_dst)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!plain || !d_dst || !count) return fail(FHE_ERR_INVALID_ARGUMENT, "bad argument");
+    const uint32_t n = c->host.n, k = c->host.k;
+    for (size_t i = 0; i < (size_t)count * n; ++i)
+        if (plain[i] >= c->host.t) return fail(FHE_ERR_INVALID_ARGUMENT, "plaintext coefficient is not below plain_modulus");
+    u64 *d_plain = nullptr;
+    const size_t bytes = (size_t)count * n * sizeof(u64);
+    CU_TRY(cudaMallocAsync(&d_plain, bytes, c->stream));
+    // A copy from pageable memory synchronises the stream (the host would wait for every queued
+    // kernel); the plaintexts go through a pinned ring instead, one slot each, so the call returns
+    // as soon as the work is queued and `plain` may be reused by the caller at once.
+    if (!c->h_ring) {
+        CU_TRY(cudaHostAlloc(&c->h_ring, (size_t)fhe_ctx::kRing * n * sizeof(u64), cudaHostAllocDefault));
+        for (int i = 0; i < fhe_ctx::kRing; ++i) CU_TRY(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
+    }
+    for (uint32_t i = 0; i < count; ++i) {
+        const int slot = (int)(c->ring_next % fhe_ctx::kRing);
+        if (c->ring_next >= (uint64_t)fhe_ctx::kRing) CU_TRY(cudaEventSynchronize(c->ev_ring[slot]));
+        ++c->ring_next;
+        u64 *h = c->h_ring + (size_t)slot * n;
+        memcpy(h, plain + (size_t)i * n, (size_t)n * sizeof(u64));
+        CU_TRY(cudaMemcpyAsync(d_plain + (size_t)i * n, h, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaEventRecord(c->ev_ring[slot], c->stream));
+    }
+    const unsigned long long total = (unsigned long long)count * 2 * k * n;
+    k_encrypt_transparent<<<grid_for(total, 256, c->sm_count), 256, 0, c->stream>>>(d_plain, (u64 *)d_dst, total, c->dev);
+    c->launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaFreeAsync(d_plain, c->stream));
+    return FHE_OK;
 }
 
 int fhe_ptab_create(fhe_ctx *c, const uint64_t *plain, uint32_t count, fhe_ptab **out)

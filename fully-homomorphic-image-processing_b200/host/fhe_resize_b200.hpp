@@ -393,6 +393,11 @@ inline void ResizeImageBatched(const CiphertextSource &load, int original_width,
             for (int ch = 0; ch < 3; ++ch) sample.push_back(out.get((size_t)x * 3 + ch));
             destImage.pixels.push_back(std::move(sample));
         }
+        // Nothing above waits for the device, so the host could queue many rows ahead; the
+        // temporaries of every queued row would then be live in the stream-ordered pool at once
+        // (gigabytes at size 6) and the pool would keep growing through the driver.  One
+        // synchronisation per output row bounds that to a row's worth.
+        check(fhe_ctx_sync(ctx.handle()));
     }
 }
 

@@ -555,14 +555,8 @@ inline void Encryptor::encrypt(const Plaintext &plain, Ciphertext &destination) 
     if (!ctx_) throw std::logic_error("this Encryptor holds no public key and no context");
     if (plain.coeffs().size() != ctx_->poly_degree()) throw std::invalid_argument("plain is not valid for encryption parameters");
     Ciphertext z(*ctx_, 2);
-    check(fhe_device_zero(ctx_->handle(), z.device_data(), ctx_->ct_words(2) * sizeof(uint64_t)));
-    if (!plain.is_zero()) {
-        fhe_ptab *t = nullptr;
-        check(fhe_ptab_create(ctx_->handle(), plain.coeffs().data(), 1, &t));
-        const int rc = fhe_add_plain(ctx_->handle(), z.device_data(), 1, 2, t, 0);
-        fhe_ptab_destroy(t);
-        check(rc);
-    }
+    if (plain.is_zero()) check(fhe_device_zero(ctx_->handle(), z.device_data(), ctx_->ct_words(2) * sizeof(uint64_t)));
+    else check(fhe_encrypt_transparent(ctx_->handle(), plain.coeffs().data(), 1, z.device_data()));
     destination = std::move(z);
 }
 

@@ -159,6 +159,12 @@ int fhe_jpeg_rgb_tiles(fhe_ctx *ctx, const fhe_jpeg_plan *plan, const uint64_t *
  * deterministic server-side Encryptor starts from (fhe_resize.h:230-266 and fhe_decode.h:54,134
  * encrypt public scalars on the server). */
 int fhe_device_zero(fhe_ctx *ctx, void *dptr, size_t bytes);
+/* The transparent (key-less, noise-free) encryption of `count` plaintexts in one call:
+ * d_dst[i] = (Delta * m_i, 0), size 2, plaintext i at plain[i * n .. ) with coefficients < t.
+ * Same ciphertext as fhe_device_zero + fhe_add_plain, without building a plaintext table (one
+ * upload, one kernel, no device synchronisation): the per-pixel fractions of fhe_resize.h:230-266
+ * are encrypted this way on the server. */
+int fhe_encrypt_transparent(fhe_ctx *ctx, const uint64_t *plain, uint32_t count, uint64_t *d_dst);
 
 /* ---- Evaluator: ciphertext x ciphertext ----------------------------------------------------
  * Evaluator::multiply(a, b) (fhe_resize.h:175-179,197-198; fhe_decode.h:71-97,235,239): BFV tensor

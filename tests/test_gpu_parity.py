@@ -254,3 +254,31 @@ def test_config1_full_size_properties(gpu, oracle_mod):
     for d in (da, db, dc):
         ctx.free(d)
     ctx.close()
+
+
+@pytest.mark.parametrize("n", [2048, 8192])
+def test_transparent_encryption_vs_oracle(gpu, oracle_mod, n):
+    """fhe_encrypt_transparent == add_plain onto an all-zero ciphertext (the oracle's restatement of
+    Evaluator::add_plain), and decrypts to the plaintext under any key."""
+    q = oracle_mod.default_coeff_modulus(n)
+    ctx, o = gpu.Context(n, q), oracle_mod.Oracle(n, q, 1 << 14, 64, 32)
+    vals = [0.375, -17.25, 255.0, 1.0 / 3.0, -0.001]
+    plains = np.stack([o.encode(v) for v in vals])
+    d = ctx.alloc(len(vals) * ctx.ct_bytes(2))
+    ctx.encrypt_transparent(plains, d)
+    got = np.empty(len(vals) * ctx.ct_words(2), dtype=np.uint64)
+    ctx.download(got, d)
+    W = ctx.ct_words(2)
+    sk, _ = o.keygen(4)
+    for i, v in enumerate(vals):
+        want = np.zeros(W, dtype=np.uint64)
+        o.add_plain(want, plains[i])
+        assert (got[i * W:(i + 1) * W] == want).all()
+        assert abs(o.decode(o.decrypt(sk, got[i * W:(i + 1) * W].copy(), 2)) - v) < 1e-8
+    # coefficients must be below t
+    bad = plains[:1].copy()
+    bad[0, 0] = 1 << 14
+    with pytest.raises(gpu.FheError):
+        ctx.encrypt_transparent(bad, d)
+    ctx.free(d)
+    ctx.close()

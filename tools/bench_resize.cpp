@@ -50,22 +50,34 @@ int main(int argc, char **argv)
             ~Quiet() { std::cout.rdbuf(old); }
         } quiet;
         for (int inter : {BICUBIC, BILINEAR}) {
-            next = 0;
+            // the first pass grows the stream-ordered memory pool through the driver (hundreds of MiB
+            // blocks at size 6: slow and noisy, and paid once per process); the second and third are
+            // the steady state a server streaming rows is in.  The best of those is reported, the
+            // first beside it.
+            double s = 1e30, first = 0;
+            uint64_t launches = 0;
             SImageData dest;
-            const uint64_t l0 = fhe_launch_count(ctx.handle());
-            ctx.sync();
-            auto t0 = std::chrono::steady_clock::now();
-            ResizeImageBatched(source, ow, oh, dest, dw, dh, inter, evaluator, encoder, encryptor);
-            ctx.sync();
-            const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            for (int rep = 0; rep < 3; ++rep) {
+                next = 0;
+                dest = SImageData{};
+                const uint64_t l0 = fhe_launch_count(ctx.handle());
+                ctx.sync();
+                auto t0 = std::chrono::steady_clock::now();
+                ResizeImageBatched(source, ow, oh, dest, dw, dh, inter, evaluator, encoder, encryptor);
+                ctx.sync();
+                const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                launches = fhe_launch_count(ctx.handle()) - l0;
+                if (rep == 0) first = sec;
+                else if (sec < s) s = sec;
+            }
             const double px = (double)dw * dh;
             std::printf("{\"what\": \"ResizeImageBatched %s, FractionalEncoder(100,100), n=%u k=%u, %dx%d -> %dx%d RGB, "
                         "synthetic ciphertexts, transparent fractions, relinearisation dbc %u (0 = none, as the reference)\", \"seconds\": %.4f, \"output_pixels_per_s\": %.2f, "
-                        "\"%s_calls_per_s\": %.1f, \"out_ct_size\": %u, \"kernel_launches\": %llu, "
+                        "\"%s_calls_per_s\": %.1f, \"first_pass_seconds\": %.4f, \"out_ct_size\": %u, \"kernel_launches\": %llu, "
                         "\"full_config3_512x512_to_256x256_estimate_s\": %.1f}\n",
                         inter == BICUBIC ? "bicubic" : "bilinear", n, ctx.coeff_mod_count(), ow, oh, dw, dh, dbc, s, px / s,
-                        inter == BICUBIC ? "Cubic" : "Linear", (inter == BICUBIC ? 15.0 : 9.0) * px / s,
-                        dest.pixels[0][0].size(), (unsigned long long)(fhe_launch_count(ctx.handle()) - l0), 65536.0 / (px / s));
+                        inter == BICUBIC ? "Cubic" : "Linear", (inter == BICUBIC ? 15.0 : 9.0) * px / s, first,
+                        dest.pixels[0][0].size(), (unsigned long long)launches, 65536.0 / (px / s));
         }
         return 0;
     } catch (const std::exception &e) {
