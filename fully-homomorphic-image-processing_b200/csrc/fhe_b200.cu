@@ -112,6 +112,40 @@ k_mulplain(const u64 *in, u64 *out, const W2 *__restrict__ table, RingDev R)
     ntt_inv_pass<LOGN, LOGE, 0, false>(tau, gin, gout, smem, itw, lp);
 }
 
+// Evaluator::multiply_plain by a plaintext with a few +-1 coefficients: the ring product is a sum
+// of signed negacyclic rotations, out[i] = sum_t s_t * in[i - e_t] (sign flipped when the index
+// wraps), exact like the NTT route and therefore the same canonical residues -- but one read and
+// one write of the polynomial and no multiplication at all.  One CTA per limb-polynomial, staged in
+// shared memory so the operation is in place.
+constexpr int SPARSE_MAX = 8;
+struct SparseTerms {
+    uint32_t n_terms;
+    uint32_t term[SPARSE_MAX];  // exponent | sign << 31
+};
+__global__ void __launch_bounds__(256) k_mulplain_sparse(u64 *data, SparseTerms T, RingDev R)
+{
+    extern __shared__ u64 spoly[];
+    const uint32_t n = R.n;
+    const size_t p = blockIdx.x;
+    const u64 q = R.limb[p % R.k].a.q;
+    u64 *g = data + p * n;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) spoly[i] = g[i];
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+        u64 acc = 0;  // < (n_terms + 1) q: every term adds a value in [0, q)
+        for (uint32_t t = 0; t < T.n_terms; ++t) {
+            const uint32_t e = T.term[t] & 0x7fffffffu;
+            const bool neg = (T.term[t] >> 31) != 0;
+            const uint32_t src = (i - e) & (n - 1);
+            const u64 v = spoly[src];
+            const bool flip = neg != (i < e);  // x^n = -1
+            acc += flip ? negmod(v, q) : v;
+        }
+        while (acc >= q) acc -= q;  // at most SPARSE_MAX - 1 subtractions
+        g[i] = acc;
+    }
+}
+
 // =============================================================================================
 // pointwise DCT (+quantize) kernel (csrc/dct.cuh)
 // =============================================================================================
@@ -390,6 +424,10 @@ struct fhe_ptab {
     W2 *d_ntt = nullptr;     // [count][k][n] Shoup pairs of NTT(lift(plain))
     u64 *d_scaled = nullptr; // [count][k][n] Delta-scaled coefficients
     std::vector<uint8_t> is_zero;
+    // plaintexts whose non-zero coefficients are all +1 or -1 (t - 1) and at most SPARSE_MAX many:
+    // exponent | sign << 31 per term; empty = not sparse.  FractionalEncoder encodings of small
+    // integers and of powers of two are like that (3 = 1 + x, 5 = 1 + x^2, 0.5 = -x^(n-1), 0.125 = -x^(n-3)).
+    std::vector<std::vector<uint32_t>> sparse;
 };
 struct fhe_dct_plan {
     fhe_ctx *ctx = nullptr;
@@ -872,6 +910,20 @@ int fhe_ptab_create(fhe_ctx *c, const uint64_t *plain, uint32_t count, fhe_ptab 
     for (uint32_t p = 0; p < count; ++p)
         for (uint32_t i = 0; i < n; ++i)
             if (plain[(size_t)p * n + i]) { t->is_zero[p] = 0; break; }
+    t->sparse.assign(count, {});
+    for (uint32_t p = 0; p < count; ++p) {
+        std::vector<uint32_t> terms;
+        bool ok = true;
+        for (uint32_t i = 0; i < n && ok; ++i) {
+            const uint64_t m = plain[(size_t)p * n + i];
+            if (!m) continue;
+            if (m == 1) terms.push_back(i);
+            else if (m == c->host.t - 1) terms.push_back(i | 0x80000000u);
+            else ok = false;
+            if (terms.size() > (size_t)SPARSE_MAX) ok = false;
+        }
+        if (ok && !terms.empty()) t->sparse[p] = std::move(terms);
+    }
     const size_t total = (size_t)count * k * n;
     CU_TRY(cudaMalloc(&t->d_ntt, total * sizeof(W2)));
     cudaError_t e = cudaMalloc(&t->d_scaled, total * sizeof(u64));
@@ -900,6 +952,17 @@ int fhe_multiply_plain(fhe_ctx *c, uint64_t *a, uint64_t n_ct, uint32_t size, co
     const uint64_t npoly = n_ct * size * c->host.k;
     if (!npoly) return FHE_OK;
     if (npoly > 0x7fffffffull) return fail(FHE_ERR_INVALID_ARGUMENT, "too many polynomials in one call");
+    if (!tab->sparse[index].empty()) {
+        SparseTerms T{};
+        T.n_terms = (uint32_t)tab->sparse[index].size();
+        for (uint32_t i = 0; i < T.n_terms; ++i) T.term[i] = tab->sparse[index][i];
+        const size_t smem = (size_t)c->host.n * sizeof(u64);
+        if (int rc = set_smem(k_mulplain_sparse, smem)) return rc;
+        k_mulplain_sparse<<<(unsigned)npoly, 256, smem, c->stream>>>((u64 *)a, T, c->dev);
+        c->launches++;
+        CU_TRY(cudaGetLastError());
+        return FHE_OK;
+    }
     const W2 *table = tab->d_ntt + (size_t)index * c->host.k * c->host.n;
 #define CALL(LN, LE) return launch_mulplain<LN, LE>(c, (const u64 *)a, (u64 *)a, table, npoly, c->stream)
     FHE_DISPATCH_LOGN(c->host.logn, CALL)

@@ -88,7 +88,10 @@ def test_evaluator_ops_vs_oracle(gpu, oracle_mod, n):
     b[:ctx.n] = a[:ctx.n]          # a - b == 0 on one limb
     a[ctx.n:ctx.n + 8] = 0         # zeros (negate keeps 0)
     enc = gpu.FractionalEncoder(n)
-    vals = [0.541196100, -1.847759065, 0.125, 3.0, 1 / 99, -128.0, 128.0, 2.0 ** -40]
+    # dense plaintexts (NTT route) and plaintexts with at most 8 coefficients, all +-1 (the signed-
+    # rotation route of fhe_multiply_plain): 3 = 1 + x, 255 = 8 terms, 511 = 9 terms (dense route again)
+    vals = [0.541196100, -1.847759065, 0.125, 3.0, 1 / 99, -128.0, 128.0, 2.0 ** -40,
+            5.0, -3.0, 7.0, 0.5, 255.0, 511.0, -2.75, 1.0]
     plains = np.stack([enc.encode(v) for v in vals] + [np.zeros(n, dtype=np.uint64)])
     tab = gpu.PlainTable(ctx, plains)
     da, db = ctx.to_device(a), ctx.to_device(b)
