@@ -28,54 +28,55 @@ inline void fresh_encrypt(Encryptor &e, const Plaintext &p, CiphertextBatch &res
 {
     e.encrypt(p, res, like.count());
 }
-// shared body: the two series differ only in the sign of every coefficient.  CT = Ciphertext (the
-// reference's call) or CiphertextBatch (the same graph on many independent arguments at once).
-// the series itself; `res` holds the fresh encryption of 0.0 on entry (fhe_decode.h:54, :134)
+// The part of a series that depends on the argument only: the sum of the five weighted powers of
+// (x - 3 pi / 2) (size 11 without relinearisation).
 template <class CT>
-inline void taylor_3pi2_core(CT &x, CT &res, double sign, Evaluator &evaluator, FractionalEncoder &encoder)
+inline CT taylor_terms(const CT &x, double sign, Evaluator &evaluator, FractionalEncoder &encoder)
 {
     CT shifted_x(x);
     evaluator.add_plain(shifted_x, encoder.encode(-3 * M_PI / 2.0));
 
+    // The reference recomputes every power from shifted_x (fhe_decode.h:66-111: 1 + 2 + 4 + 3 + 5 = 15
+    // ciphertext products); Evaluator::square / multiply are deterministic, so square(shifted_x) is
+    // the same ciphertext every time it is formed and the chain below -- x^2, x^4, x^8 once, x^6 and
+    // x^10 from x^4 and x^8 -- gives bit-identical terms with 7 products.
     CT power2(shifted_x);
-    CT power4(shifted_x);
-    CT power6(shifted_x);
-    CT power8(shifted_x);
-    CT power10(shifted_x);
+    evaluator.square(power2);                 // x^2
+    CT power4(power2);
+    evaluator.square(power4);                 // x^4 = square(square(x))
+    CT power8(power4);
+    evaluator.square(power8);                 // x^8
+    CT power6(power4);
+    evaluator.multiply(power6, shifted_x);
+    evaluator.multiply(power6, shifted_x);    // x^6 = (x^4 * x) * x
+    CT power10(power8);
+    evaluator.multiply(power10, shifted_x);
+    evaluator.multiply(power10, shifted_x);   // x^10 = (x^8 * x) * x
 
-    // 2nd order term
-    evaluator.square(power2);
     evaluator.multiply_plain(power2, encoder.encode(sign * 0.5));
-    // 4th order term
-    evaluator.square(power4);
-    evaluator.square(power4);
     evaluator.multiply_plain(power4, encoder.encode(sign * (-1.0 / 24.0)));
-    // 6th order term
-    evaluator.square(power6);
-    evaluator.square(power6);
-    evaluator.multiply(power6, shifted_x);
-    evaluator.multiply(power6, shifted_x);
     evaluator.multiply_plain(power6, encoder.encode(sign * (1.0 / 720.0)));
-    // 8th order term
-    evaluator.square(power8);
-    evaluator.square(power8);
-    evaluator.square(power8);
     evaluator.multiply_plain(power8, encoder.encode(sign * (-1.0 / 40320.0)));
-    // 10th order term
-    evaluator.square(power10);
-    evaluator.square(power10);
-    evaluator.square(power10);
-    evaluator.multiply(power10, shifted_x);
-    evaluator.multiply(power10, shifted_x);
     evaluator.multiply_plain(power10, encoder.encode(sign * (1.0 / 3628800.0)));
 
-    // 0th order term and the sum
-    evaluator.add_plain(res, encoder.encode(sign * -1.0));
-    evaluator.add(res, power2);
-    evaluator.add(res, power4);
-    evaluator.add(res, power6);
-    evaluator.add(res, power8);
-    evaluator.add(res, power10);
+    // ciphertext addition is exact modular addition per coefficient, hence associative: summing the
+    // terms first and adding the fresh encryption afterwards gives the bits of the reference's
+    // ((((res + 1) + p2) + p4) + ...) chain
+    evaluator.add(power10, power2);
+    evaluator.add(power10, power4);
+    evaluator.add(power10, power6);
+    evaluator.add(power10, power8);
+    return power10;
+}
+// shared body: the two series differ only in the sign of every coefficient.  CT = Ciphertext (the
+// reference's call) or CiphertextBatch (the same graph on many independent arguments at once).
+// `res` holds the fresh encryption of 0.0 on entry (fhe_decode.h:54, :134)
+template <class CT>
+inline void taylor_3pi2_core(CT &x, CT &res, double sign, Evaluator &evaluator, FractionalEncoder &encoder)
+{
+    const CT terms = taylor_terms(x, sign, evaluator, encoder);
+    evaluator.add_plain(res, encoder.encode(sign * -1.0));   // 0th order term
+    evaluator.add(res, terms);
 }
 template <class CT>
 inline void taylor_3pi2(CT &x, CT &res, double sign, Evaluator &evaluator, FractionalEncoder &encoder,
@@ -174,7 +175,7 @@ inline void approximated_step_batched(Ciphertext &amplitude, Ciphertext &index, 
         }
         return;
     }
-    CiphertextBatch sin_arg(ctx, E, 2), cos_arg(ctx, E, 2), sin_f(ctx, E, 2), cos_f(ctx, E, 2);
+    CiphertextBatch cos_arg(ctx, E, 2), sin_f(ctx, E, 2), cos_f(ctx, E, 2);
     Ciphertext z;
     for (size_t i = 0; i < npos; ++i)
         for (int j = 1; j <= degree; ++j) {
@@ -186,15 +187,30 @@ inline void approximated_step_batched(Ciphertext &amplitude, Ciphertext &index, 
             encryptor.encrypt(encoder.encode(0.0), z);                // homomorphic_cos's res (:134)
             cos_f.set(e, z);
         }
+    // The sine argument b * j pi / order does not depend on the position (fhe_decode.h:224-226): its
+    // powers and their weighted sum are the same ciphertexts for every i, so they are formed once per
+    // j (`degree` series instead of width * height * degree); only the fresh encryption each
+    // homomorphic_sin starts from differs per call and is added per element below.
+    CiphertextBatch sin_args(ctx, (size_t)degree, 2);
     for (int j = 1; j <= degree; ++j) {
         const double arg_factor = ((float)j) * M_PI / ((double)order);
         Ciphertext sa(b);
         evaluator.multiply_plain(sa, encoder.encode(arg_factor));     // the same ciphertext for every i
-        for (size_t i = 0; i < npos; ++i) sin_arg.set((size_t)(j - 1) * npos + i, sa);
+        sin_args.set((size_t)(j - 1), sa);
         CiphertextBatch cj = cos_arg.slice((size_t)(j - 1) * npos, npos);
         evaluator.multiply_plain(cj, encoder.encode(arg_factor));     // in place on the slice
     }
-    detail::taylor_3pi2_core(sin_arg, sin_f, 1.0, evaluator, encoder);
+    {
+        const CiphertextBatch sin_terms = detail::taylor_terms(sin_args, 1.0, evaluator, encoder);
+        CiphertextBatch rep(ctx, E, sin_terms.size());
+        for (int j = 1; j <= degree; ++j) {
+            const Ciphertext tj = sin_terms.get((size_t)(j - 1));
+            for (size_t i = 0; i < npos; ++i) rep.set((size_t)(j - 1) * npos + i, tj);
+        }
+        evaluator.add_plain(sin_f, encoder.encode(-1.0));              // res + (-1), per element
+        evaluator.add(rep, sin_f);                                     // + the shared terms
+        sin_f = std::move(rep);
+    }
     detail::taylor_3pi2_core(cos_arg, cos_f, -1.0, evaluator, encoder);
     evaluator.multiply(sin_f, cos_f);                                  // term = sin_factor * cos_factor
     CiphertextBatch c(ctx, npos, 2);

@@ -28,5 +28,5 @@ assert all(p.returncode == 0 for p in procs), [p.returncode for p in procs]
 per = [json.loads(o.strip().splitlines()[-1]) for o in outs]
 secs = [r["seconds_per_run_length_pair"] for r in per]
 print(json.dumps({"what": per[0]["what"], "n_gpus": a.gpus, "pairs_per_s": sum(1.0 / s for s in secs),
-                  "seconds_per_pair_per_gpu": secs, "ct_products_per_s": sum(r["ct_products_per_s"] for r in per),
+                  "seconds_per_pair_per_gpu": secs, "reference_graph_ct_products_per_s": sum(r["reference_graph_ct_products_per_s"] for r in per),
                   "out_ct_size": per[0]["out_ct_size"], "wall_s_including_setup": wall}))
