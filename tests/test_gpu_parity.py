@@ -285,3 +285,22 @@ def test_transparent_encryption_vs_oracle(gpu, oracle_mod, n):
         ctx.encrypt_transparent(bad, d)
     ctx.free(d)
     ctx.close()
+
+
+def test_device_block_cache(gpu, oracle_mod):
+    """fhe_device_alloc / fhe_device_free keep freed blocks for exact-size reuse: same size -> same
+    block back, a second free of a parked block and a foreign pointer are refused."""
+    ctx = gpu.Context(2048, oracle_mod.default_coeff_modulus(2048))
+    a = ctx.alloc(1 << 20)
+    ctx.free(a)
+    b = ctx.alloc(1 << 20)
+    assert b == a                      # handed out again without touching the driver
+    c = ctx.alloc(1 << 20)
+    assert c != b
+    ctx.free(b)
+    with pytest.raises(gpu.FheError):
+        ctx.free(b)                    # double free
+    with pytest.raises(gpu.FheError):
+        ctx.free(c + 256)              # not a block of this allocator
+    ctx.free(c)
+    ctx.close()
