@@ -157,6 +157,57 @@ def test_quantised_stream_matches_a_standard_encoder(tmp_path, pkg):
     assert rms_pair < 0.25 * rms_ref, (rms_pair, rms_ref)
 
 
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "ref_jpeg_harness")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def reference_rms(a, b):
+    """compare_jpeg_jojpeg (fhe_image.h:514-519): int accumulator, sqrt of the mean, printed with %g."""
+    d = a.astype(np.int64) - b.astype(np.int64)
+    return format(float(np.sqrt(float((d * d).sum()) / d.size)), "g")
+
+
+def decode_like_the_reference(path, tmp):
+    """stb_image, the decoder the reference's number was measured with, when oracle/_ref is built
+    (make -C oracle ref; needs /root/reference at build time only); PIL otherwise."""
+    if os.path.exists(HARNESS):
+        out = os.path.join(tmp, "dec.rgb")
+        w, h = map(int, subprocess.check_output([HARNESS, "decode", path, out]).split())
+        return np.fromfile(out, dtype=np.uint8).reshape(h, w, 3), True
+    return decode_rgb(path), False
+
+
+def boazbarak():
+    import json
+    meta = json.load(open(os.path.join(GOLDEN, "jpeg_golden.json")))
+    shape = (meta["height"], meta["width"], 3)
+    img = np.fromfile(os.path.join(GOLDEN, "boazbarak_rgb.bin"), dtype=np.uint8).reshape(shape)
+    jo = np.fromfile(os.path.join(GOLDEN, "boazbarak_jo_q0_rgb.bin"), dtype=np.uint8).reshape(shape)
+    return img, jo, meta
+
+
+def check_published_rms(values, tmp_path):
+    """values: [tile][3][64] decoded server outputs for image/boazbarak.jpg -> the reference's RMSError line"""
+    img, jo, meta = boazbarak()
+    h, w, _ = img.shape
+    got, exact_decoder = decode_like_the_reference(pack(values, w, h, 0, str(tmp_path / "fhe.jpg")), str(tmp_path))
+    rms = reference_rms(got, jo)
+    if exact_decoder:
+        assert rms == meta["published_rms_error"], rms          # 1.71767, benchmark/results.txt:37-42
+    else:
+        assert abs(float(rms) - float(meta["published_rms_error"])) < 0.1, rms
+    return rms
+
+
+def test_reference_published_rms_error(tmp_path):
+    """The one end-to-end number the reference publishes for the JPEG path:
+    RMSError 1.71767 between the picture decoded from the homomorphic pipeline's JPEG and jo_jpeg's
+    (benchmark/results.txt:37-42, image/boazbarak.jpg), reproduced digit for digit from the committed
+    fixtures by the plaintext mirror of the pipeline + this repo's JPEG writer."""
+    img, _, _ = boazbarak()
+    check_published_rms(plaintext_pipeline(img), tmp_path)
+
+
 def test_rms_tool_and_rounding(tmp_path):
     a = np.arange(48, dtype=np.uint8)
     b = a.copy()

@@ -143,3 +143,40 @@ def test_server_jpeg_end_to_end_on_gpu(pkg, oracle_mod, tmp_path):
     rgb = decode_rgb(pack(values, width, height, 0, str(tmp_path / "fhe.jpg")))
     rms = float(np.sqrt(np.mean((rgb.astype(float) - image.astype(float)) ** 2)))
     assert rms < 1.5, rms
+
+
+@pytest.mark.gpu
+def test_published_rms_error_through_the_encrypted_pipeline(pkg, oracle_mod, tmp_path):
+    """image/boazbarak.jpg (48 x 48, committed fixture) -> client-side encryption of every pixel
+    (oracle harness) -> server_jpeg_b200 on the GPU -> decryption -> this repo's JPEG writer ->
+    the reference's decoder and comparator: RMSError 1.71767, the number the reference publishes
+    for its own pipeline (benchmark/results.txt:37-42)."""
+    from test_client_jpeg import boazbarak, check_published_rms
+    exe = build_exe(pkg)
+    image, _, _ = boazbarak()
+    height, width, _ = image.shape
+    n = 4096
+    q = oracle_mod.default_coeff_modulus(n)
+    o = oracle_mod.Oracle(n, q, 1 << 14)
+    k = o.k
+    sk, pk = o.keygen(48)
+    os.makedirs(tmp_path / "keys")
+    os.makedirs(tmp_path / "image")
+    (tmp_path / "keys" / "params.txt").write_text(f"{width} {height} 3 {1 << 14}\n")
+    seed = 1
+    with open(tmp_path / "image" / "nothingpersonnel.txt", "wb") as f:
+        for by in range(height // 8):
+            for bx in range(width // 8):
+                blk = image[8 * by:8 * by + 8, 8 * bx:8 * bx + 8].reshape(64, 3)
+                for c in range(3):
+                    for p in range(64):
+                        wire_save(f, o.encrypt(pk, o.encode(float(blk[p, c])), seed), 2, k, n)
+                        seed += 1
+    r = subprocess.run([exe, "--cmod", str(n), "--pmod", str(1 << 14)], capture_output=True, text=True,
+                       cwd=tmp_path, timeout=1800)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = wire_load_all(tmp_path / "image" / "zoop.txt", k, n)
+    tiles = (height // 8) * (width // 8)
+    assert len(got) == tiles * 192
+    values = np.array([o.decode(o.decrypt(sk, ct, 2)) for ct in got]).reshape(tiles, 3, 64)
+    check_published_rms(values, tmp_path)
