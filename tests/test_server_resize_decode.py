@@ -141,3 +141,33 @@ def test_server_decode_matches_oracle_on_gpu(pkg, oracle_mod, tmp_path):
         for ch in range(3):
             assert got[p * 3 + ch].size == chans[ch][p].size
             assert (got[p * 3 + ch] == chans[ch][p]).all(), (p, ch)
+
+
+@pytest.mark.gpu
+def test_published_bilinear_rms_error_through_the_encrypted_pipeline(pkg, oracle_mod, tmp_path):
+    """image/boazbarak.jpg (48 x 48 fixture) -> every sample encrypted (oracle harness) ->
+    server_resize_b200 (bilinear, 17 x 17) on the GPU -> decryption of the size-4 results ->
+    int(decode), CLAMP -> the reference's comparator against OpenCV's resize: RMSError 17.9597, the
+    number the reference publishes for its own pipeline (benchmark/results.txt, 30 parameter sets)."""
+    from test_resize_published import client_pixels, fixtures, reference_rms
+    exe = resize_exe(pkg)
+    img, lin, _, r = fixtures()
+    oh, ow, _ = img.shape
+    dw, dh = r["width"], r["height"]
+    n = 4096
+    o = oracle_mod.Oracle(n, oracle_mod.default_coeff_modulus(n), 1 << 14)
+    k = o.k
+    sk, pk = o.keygen(17)
+    os.makedirs(tmp_path / "keys")
+    os.makedirs(tmp_path / "image")
+    (tmp_path / "keys" / "params.txt").write_text(f"{ow} {oh} 3 16384\n")
+    with open(tmp_path / "image" / "nothingpersonnel.txt", "wb") as f:      # client_resize --send: RGB interleaved, row major
+        for i, v in enumerate(img.reshape(-1)):
+            wire_save(f, o.encrypt(pk, o.encode(float(v)), i + 1), 2, k, n)
+    res = subprocess.run([exe, "-w", str(dw), "-h", str(dh), "--cmod", str(n)], capture_output=True, text=True,
+                         cwd=tmp_path, timeout=1800)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    got = wire_load_all(tmp_path / "image" / "zoop.txt", k, n)
+    assert len(got) == dw * dh * 3 and all(g.size == o.ct_words(4) for g in got)
+    values = np.array([o.decode(o.decrypt(sk, ct, 4)) for ct in got]).reshape(dh, dw, 3)
+    assert reference_rms(client_pixels(values), lin) == r["published_rms_error_bilinear"]
