@@ -19,7 +19,14 @@
  *   homo/fhe_image.h:310-325  rgb_to_ycc_fhe     -> orc_rgb_to_ycc_fhe
  *   homo/server_jpeg.cpp:74-80,100  parameters   -> orc_ctx_create / encoder
  * It is cross-checked against an independent pure-Python big-int model
- * (oracle/pymodel.py) and algebraic identities (Dec o Eval == Eval_plain).
+ * (oracle/pymodel.py) and algebraic identities (Dec o Eval == Eval_plain), and
+ * -- at the level of decrypted results, the only level at which the reference
+ * pins anything -- against every number the reference holds for this path:
+ *   tests/parameters.cpp:100-128   42x^3 - 27x + 1 at 12345 = 79017370138936
+ *   benchmark/results.txt:37-42    JPEG pipeline RMSError 1.71767 (boazbarak.jpg)
+ *   benchmark/results.txt:17-21    bilinear resize RMSError 17.9597
+ * (tests/test_reference_known_answers.py, test_client_jpeg.py, test_resize_published.py
+ * and their GPU counterparts).  Ciphertext BITS remain unpinned: SEAL is absent.
  *
  * Ciphertext layout everywhere: [poly][limb][n] u64, residues in [0, q_limb).
  * (SEAL 2.3 stores n+1 coefficients per limb with a zero top coefficient; the
