@@ -109,6 +109,7 @@ def lib():
         "fhe_jpeg_rgb_tiles": (i32, [vp, vp, vp, vp, u64]),
         "fhe_device_zero": (i32, [vp, vp, C.c_size_t]),
         "fhe_encrypt_transparent": (i32, [vp, u64p, u32, vp]),
+        "fhe_ntt_loge": (u32, [u32]),
         "fhe_multiply": (i32, [vp, vp, u32, vp, u32, vp, u64]),
         "fhe_square": (i32, [vp, vp, u32, vp, u64]),
         "fhe_evk_digits": (u32, [vp, u32]),
@@ -131,7 +132,7 @@ EXPORTED_SYMBOLS = (
     "fhe_ntt_forward", "fhe_ntt_inverse", "fhe_dct_plan_create", "fhe_dct_plan_destroy",
     "fhe_dct8x8_quantize", "fhe_dct8x8_quantize_host", "fhe_fill_uniform", "fhe_checksum",
     "fhe_launch_count", "fhe_set_dct_chunk_blocks", "fhe_set_stage_timing", "fhe_get_stage_times",
-    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_encrypt_transparent", "fhe_multiply", "fhe_square", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
+    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_encrypt_transparent", "fhe_ntt_loge", "fhe_multiply", "fhe_square", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
 )
 
 

@@ -223,7 +223,6 @@ template <int LOGN, int LOGE>
 __global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_nttw_fwd(const u64 *in, u64 *out, WideRing R)
 {
     using S = NttShape<LOGN, LOGE>;
-    static_assert(S::NPASS == 3, "pass chain written for 3 passes");
     extern __shared__ u64 smem[];
     const size_t p = blockIdx.x;
     const int j = (int)(p % R.nb), tau = threadIdx.x;
@@ -236,12 +235,17 @@ __global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_nttw_fwd(const u64 *in, 
     nttw_fwd_pass<LOGN, LOGE, 1>(tau, gin, gout, smem, tw, lp);
     __syncthreads();
     nttw_fwd_pass<LOGN, LOGE, 2>(tau, gin, gout, smem, tw, lp);
+    if constexpr (S::NPASS == 4) {
+        __syncthreads();
+        nttw_fwd_pass<LOGN, LOGE, 3>(tau, gin, gout, smem, tw, lp);
+    }
+    static_assert(S::NPASS == 3 || S::NPASS == 4, "3 or 4 passes");
 }
 template <int LOGN, int LOGE>
 __global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_nttw_inv(const u64 *in, u64 *out, WideRing R)
 {
     using S = NttShape<LOGN, LOGE>;
-    static_assert(S::NPASS == 3, "pass chain written for 3 passes");
+    static_assert(S::NPASS == 3 || S::NPASS == 4, "3 or 4 passes");
     extern __shared__ u64 smem[];
     const size_t p = blockIdx.x;
     const int j = (int)(p % R.nb), tau = threadIdx.x;
@@ -249,6 +253,10 @@ __global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_nttw_inv(const u64 *in, 
     u64 *gout = out + p * S::N;
     const W2 *itw = R.itw + (size_t)j * S::N;
     const LimbWide lp = R.limb[j];
+    if constexpr (S::NPASS == 4) {
+        nttw_inv_pass<LOGN, LOGE, 3>(tau, gin, gout, smem, itw, lp);
+        __syncthreads();
+    }
     nttw_inv_pass<LOGN, LOGE, 2>(tau, gin, gout, smem, itw, lp);
     __syncthreads();
     nttw_inv_pass<LOGN, LOGE, 1>(tau, gin, gout, smem, itw, lp);

@@ -116,8 +116,8 @@ inline bool build_behz(const HostRing &R, HostBehz &H, std::string &err)
         case 10: ntt_permute_table<10, 4>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<10, 4>(seal_itw.data(), H.itw[j].data()); break;
         case 11: ntt_permute_table<11, 4>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<11, 4>(seal_itw.data(), H.itw[j].data()); break;
         case 12: ntt_permute_table<12, 4>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<12, 4>(seal_itw.data(), H.itw[j].data()); break;
-        case 13: ntt_permute_table<13, 5>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<13, 5>(seal_itw.data(), H.itw[j].data()); break;
-        case 14: ntt_permute_table<14, 5>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<14, 5>(seal_itw.data(), H.itw[j].data()); break;
+        case 13: ntt_permute_table<13, FHE_LOGE13>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<13, FHE_LOGE13>(seal_itw.data(), H.itw[j].data()); break;
+        case 14: ntt_permute_table<14, FHE_LOGE14>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<14, FHE_LOGE14>(seal_itw.data(), H.itw[j].data()); break;
         }
         const u64 ninv = h_invmod(n % p, p);
         L.ninv = h_shoup64(ninv, p);

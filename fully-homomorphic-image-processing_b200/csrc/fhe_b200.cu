@@ -45,7 +45,7 @@ template <int LOGN, int LOGE, int OUT>
 __global__ void __launch_bounds__(1 << (LOGN - LOGE), NTT_MIN_CTAS(LOGN, LOGE)) k_ntt_fwd(const u64 *in, u64 *out, RingDev R)
 {
     using S = NttShape<LOGN, LOGE>;
-    static_assert(S::NPASS == 3, "pass chain written for 3 passes");
+    constexpr int LAST = S::NPASS - 1;
     extern __shared__ u64 smem[];
     const size_t p = blockIdx.x;
     const int j = (int)(p % R.k), tau = threadIdx.x;
@@ -53,18 +53,15 @@ __global__ void __launch_bounds__(1 << (LOGN - LOGE), NTT_MIN_CTAS(LOGN, LOGE)) 
     u64 *gout = out + p * S::N;
     const W2 *tw = R.tw + (size_t)j * S::N;
     const LimbDev lp = R.limb[j];
-    ntt_fwd_pass<LOGN, LOGE, 0, OUT>(tau, gin, gout, smem, tw, lp);
-    __syncthreads();
-    ntt_fwd_pass<LOGN, LOGE, 1, OUT>(tau, gin, gout, smem, tw, lp);
-    __syncthreads();
-    ntt_fwd_pass<LOGN, LOGE, 2, OUT>(tau, gin, gout, smem, tw, lp);
+    ntt_fwd_passes<LOGN, LOGE, OUT, 0, LAST>(tau, gin, gout, smem, tw, lp);
+    ntt_fwd_pass<LOGN, LOGE, LAST, OUT>(tau, gin, gout, smem, tw, lp);
 }
 
 template <int LOGN, int LOGE, bool SCALE>
 __global__ void __launch_bounds__(1 << (LOGN - LOGE), NTT_MIN_CTAS(LOGN, LOGE)) k_ntt_inv(const u64 *in, u64 *out, RingDev R)
 {
     using S = NttShape<LOGN, LOGE>;
-    static_assert(S::NPASS == 3, "pass chain written for 3 passes");
+    constexpr int LAST = S::NPASS - 1;
     extern __shared__ u64 smem[];
     const size_t p = blockIdx.x;
     const int j = (int)(p % R.k), tau = threadIdx.x;
@@ -72,11 +69,8 @@ __global__ void __launch_bounds__(1 << (LOGN - LOGE), NTT_MIN_CTAS(LOGN, LOGE)) 
     u64 *gout = out + p * S::N;
     const W2 *itw = R.itw + (size_t)j * S::N;
     const LimbDev lp = R.limb[j];
-    ntt_inv_pass<LOGN, LOGE, 2, SCALE>(tau, gin, gout, smem, itw, lp);
-    __syncthreads();
-    ntt_inv_pass<LOGN, LOGE, 1, SCALE>(tau, gin, gout, smem, itw, lp);
-    __syncthreads();
-    ntt_inv_pass<LOGN, LOGE, 0, SCALE>(tau, gin, gout, smem, itw, lp);
+    ntt_inv_pass<LOGN, LOGE, LAST, SCALE>(tau, gin, gout, smem, itw, lp);
+    ntt_inv_passes<LOGN, LOGE, SCALE, LAST - 1, 0>(tau, gin, gout, smem, itw, lp);
 }
 
 // Evaluator::multiply_plain as ONE kernel per limb-poly: forward NTT (lazy), dyadic product with
@@ -87,7 +81,7 @@ __global__ void __launch_bounds__(1 << (LOGN - LOGE))
 k_mulplain(const u64 *in, u64 *out, const W2 *__restrict__ table, RingDev R)
 {
     using S = NttShape<LOGN, LOGE>;
-    static_assert(S::NPASS == 3, "pass chain written for 3 passes");
+    constexpr int LAST = S::NPASS - 1;
     extern __shared__ u64 smem[];
     const size_t p = blockIdx.x;
     const int j = (int)(p % R.k), tau = threadIdx.x;
@@ -96,21 +90,15 @@ k_mulplain(const u64 *in, u64 *out, const W2 *__restrict__ table, RingDev R)
     const W2 *tw = R.tw + (size_t)j * S::N, *itw = R.itw + (size_t)j * S::N;
     const W2 *tab = table + (size_t)j * S::N;
     const LimbDev lp = R.limb[j];
-    ntt_fwd_pass<LOGN, LOGE, 0, NTT_OUT_LAZY>(tau, gin, gout, smem, tw, lp);
-    __syncthreads();
-    ntt_fwd_pass<LOGN, LOGE, 1, NTT_OUT_LAZY>(tau, gin, gout, smem, tw, lp);
-    __syncthreads();
+    ntt_fwd_passes<LOGN, LOGE, NTT_OUT_LAZY, 0, LAST>(tau, gin, gout, smem, tw, lp);
     u64 v[S::E];
-    ntt_fwd_load<LOGN, LOGE, 2>(v, tau, gin, smem);
-    ntt_fwd_compute<LOGN, LOGE, 2>(v, tau, tw, lp);
+    ntt_fwd_load<LOGN, LOGE, LAST>(v, tau, gin, smem);
+    ntt_fwd_compute<LOGN, LOGE, LAST>(v, tau, tw, lp);
 #pragma unroll
     for (int e = 0; e < S::E; ++e) v[e] = mulc(v[e], tab[e * S::T + tau], lp.a.n2q);
-    ntt_inv_compute<LOGN, LOGE, 2, false>(v, tau, itw, lp);
-    ntt_inv_store<LOGN, LOGE, 2>(v, tau, gout, smem);
-    __syncthreads();
-    ntt_inv_pass<LOGN, LOGE, 1, false>(tau, gin, gout, smem, itw, lp);
-    __syncthreads();
-    ntt_inv_pass<LOGN, LOGE, 0, false>(tau, gin, gout, smem, itw, lp);
+    ntt_inv_compute<LOGN, LOGE, LAST, false>(v, tau, itw, lp);
+    ntt_inv_store<LOGN, LOGE, LAST>(v, tau, gout, smem);
+    ntt_inv_passes<LOGN, LOGE, false, LAST - 1, 0>(tau, gin, gout, smem, itw, lp);
 }
 
 // Evaluator::multiply_plain by a plaintext with a few +-1 coefficients: the ring product is a sum
@@ -469,8 +457,8 @@ static int set_smem(K kernel, size_t bytes)
     case 10: { CALL(10, 4); } break;                               \
     case 11: { CALL(11, 4); } break;                               \
     case 12: { CALL(12, 4); } break;                               \
-    case 13: { CALL(13, 5); } break;                               \
-    case 14: { CALL(14, 5); } break;                               \
+    case 13: { CALL(13, FHE_LOGE13); } break;                               \
+    case 14: { CALL(14, FHE_LOGE14); } break;                               \
     default: return fail(FHE_ERR_UNSUPPORTED, "unsupported ring degree"); \
     }
 
@@ -843,6 +831,15 @@ int fhe_add(fhe_ctx *c, uint64_t *a, const uint64_t *b, uint64_t n_ct, uint32_t 
 int fhe_sub(fhe_ctx *c, uint64_t *a, const uint64_t *b, uint64_t n_ct, uint32_t size) { return elementwise(c, 1, (u64 *)a, (const u64 *)b, n_ct, size); }
 int fhe_negate(fhe_ctx *c, uint64_t *a, uint64_t n_ct, uint32_t size) { return elementwise(c, 2, (u64 *)a, nullptr, n_ct, size); }
 
+uint32_t fhe_ntt_loge(uint32_t n)
+{
+    switch (n) {
+    case 1024: case 2048: case 4096: return 4;
+    case 8192: return FHE_LOGE13;
+    case 16384: return FHE_LOGE14;
+    default: return 0;
+    }
+}
 int fhe_ntt_forward(fhe_ctx *c, uint64_t *a, uint64_t npoly)
 {
     if (int rc = check_ctx(c)) return rc;

@@ -33,6 +33,18 @@ struct LimbDev {
     W2 iw1;      // itw[1] (inverse transform whose n^-1 is folded into a preceding table)
 };
 
+// coefficients per thread (2^LOGE) of the transforms of degree 2^13 and 2^14 in this build: every
+// kernel, table and test takes it from here.  4: four passes, 64 registers, 1024 threads per SM;
+// 5: three passes, 128 registers, 512 threads per SM.  Measured equal at n = 8192 (the fourth
+// shared-memory exchange costs what the occupancy gains: multiply_plain 0.295 vs 0.302 ms per 256
+// ciphertexts, multiply 2.41 vs 2.38, square 1.88 vs 1.82; profiles/r01_notes.md) -- 5 is kept.
+#ifndef FHE_LOGE13
+#define FHE_LOGE13 5
+#endif
+#ifndef FHE_LOGE14
+#define FHE_LOGE14 5
+#endif
+
 constexpr int FHE_BMAX = 256;   // q < 2^55  =>  256 q <= 2^63
 constexpr int FHE_MULC_B = 5;   // mulc output bound (units of q)
 constexpr int FHE_RED_B = 4;    // reduce63 output bound
@@ -282,6 +294,29 @@ FHE_HD void ntt_inv_pass(int tau, const u64 *gin, u64 *gout, u64 *smem, const W2
     ntt_inv_compute<LOGN, LOGE, P, SCALE>(v, tau, itw, lp);
     ntt_inv_store<LOGN, LOGE, P>(v, tau, gout, smem);
 }
+
+#if defined(__CUDACC__)
+// Pass chains for the kernels: forward passes P .. PEND-1 with a barrier after each; inverse passes
+// P down to PEND with a barrier before each.
+template <int LOGN, int LOGE, int OUT, int P, int PEND>
+__device__ __forceinline__ void ntt_fwd_passes(int tau, const u64 *gin, u64 *gout, u64 *smem, const W2 *tw, const LimbDev &lp)
+{
+    if constexpr (P < PEND) {
+        ntt_fwd_pass<LOGN, LOGE, P, OUT>(tau, gin, gout, smem, tw, lp);
+        __syncthreads();
+        ntt_fwd_passes<LOGN, LOGE, OUT, P + 1, PEND>(tau, gin, gout, smem, tw, lp);
+    }
+}
+template <int LOGN, int LOGE, bool SCALE, int P, int PEND>
+__device__ __forceinline__ void ntt_inv_passes(int tau, const u64 *gin, u64 *gout, u64 *smem, const W2 *itw, const LimbDev &lp)
+{
+    if constexpr (P >= PEND) {
+        __syncthreads();
+        ntt_inv_pass<LOGN, LOGE, P, SCALE>(tau, gin, gout, smem, itw, lp);
+        ntt_inv_passes<LOGN, LOGE, SCALE, P - 1, PEND>(tau, gin, gout, smem, itw, lp);
+    }
+}
+#endif
 
 // Host: permute a SEAL-order root-power table (index m + i) into the per-pass layout.
 template <int LOGN, int LOGE, int P = 0>

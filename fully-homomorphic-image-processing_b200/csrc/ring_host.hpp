@@ -139,8 +139,8 @@ inline bool build_ring(HostRing &R, uint32_t n, uint32_t k, const uint64_t *q, u
         case 10: ntt_permute_table<10, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<10, 4>(seal_itw.data(), L.itw.data()); break;
         case 11: ntt_permute_table<11, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<11, 4>(seal_itw.data(), L.itw.data()); break;
         case 12: ntt_permute_table<12, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<12, 4>(seal_itw.data(), L.itw.data()); break;
-        case 13: ntt_permute_table<13, 5>(seal_tw.data(), L.tw.data()); ntt_permute_table<13, 5>(seal_itw.data(), L.itw.data()); break;
-        case 14: ntt_permute_table<14, 5>(seal_tw.data(), L.tw.data()); ntt_permute_table<14, 5>(seal_itw.data(), L.itw.data()); break;
+        case 13: ntt_permute_table<13, FHE_LOGE13>(seal_tw.data(), L.tw.data()); ntt_permute_table<13, FHE_LOGE13>(seal_itw.data(), L.itw.data()); break;
+        case 14: ntt_permute_table<14, FHE_LOGE14>(seal_tw.data(), L.tw.data()); ntt_permute_table<14, FHE_LOGE14>(seal_itw.data(), L.itw.data()); break;
         }
         u64 ninv = h_invmod(n % qj, qj);
         L.itw1 = seal_itw[1].w;

@@ -113,6 +113,10 @@ int fhe_sub_plain(fhe_ctx *ctx, uint64_t *a, uint64_t n_ct, uint32_t size, const
  * [limb-cycled] polynomials, in place.  The NTT-domain coefficient order is internal to this
  * library (a fixed permutation of SEAL's bit-reversed order, see csrc/ntt.cuh). */
 int fhe_ntt_forward(fhe_ctx *ctx, uint64_t *a, uint64_t n_limbpolys);
+/* That permutation, for callers that want to look at NTT-domain data (the parity tests do): SEAL's
+ * scrambled index j is stored at position (j mod E) * (n / E) + j div E with E = 2^fhe_ntt_loge(n),
+ * the number of coefficients a thread keeps in registers.  0 for an unsupported n. */
+uint32_t fhe_ntt_loge(uint32_t n);
 int fhe_ntt_inverse(fhe_ctx *ctx, uint64_t *a, uint64_t n_limbpolys);
 
 /* ---- the north-star path: encrypted 8x8 DCT + quantize ------------------------------------

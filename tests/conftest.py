@@ -67,8 +67,10 @@ def emu_lib():
 
 def ntt_perm(n):
     """device NTT-domain position of SEAL scrambled index j (csrc/ntt.cuh)."""
+    import importlib
     import numpy as np
-    loge = 4 if n <= 4096 else 5
+    loge = int(importlib.import_module(PKG_NAME).lib().fhe_ntt_loge(n))   # the library's own statement of its layout
+    assert loge
     e, t = 1 << loge, n >> loge
     j = np.arange(n)
     return (j % e) * t + j // e

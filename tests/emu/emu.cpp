@@ -63,8 +63,8 @@ static int fwd_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, int m
     case 10: emu_fwd<10, 4>(L, in, out, mode); return 0;
     case 11: emu_fwd<11, 4>(L, in, out, mode); return 0;
     case 12: emu_fwd<12, 4>(L, in, out, mode); return 0;
-    case 13: emu_fwd<13, 5>(L, in, out, mode); return 0;
-    case 14: emu_fwd<14, 5>(L, in, out, mode); return 0;
+    case 13: emu_fwd<13, FHE_LOGE13>(L, in, out, mode); return 0;
+    case 14: emu_fwd<14, FHE_LOGE14>(L, in, out, mode); return 0;
     default: return -1;
     }
 }
@@ -75,8 +75,8 @@ static int inv_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, bool 
     case 10: emu_inv<10, 4>(L, in, out, scale); return 0;
     case 11: emu_inv<11, 4>(L, in, out, scale); return 0;
     case 12: emu_inv<12, 4>(L, in, out, scale); return 0;
-    case 13: emu_inv<13, 5>(L, in, out, scale); return 0;
-    case 14: emu_inv<14, 5>(L, in, out, scale); return 0;
+    case 13: emu_inv<13, FHE_LOGE13>(L, in, out, scale); return 0;
+    case 14: emu_inv<14, FHE_LOGE14>(L, in, out, scale); return 0;
     default: return -1;
     }
 }
@@ -89,12 +89,16 @@ static void emu_fwd_w(const HostBehz &H, int j, const u64 *in, u64 *out)
     for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 0>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
     for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 1>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
     for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 2>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
+    if constexpr (S::NPASS == 4)
+        for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 3>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
 }
 template <int LOGN, int LOGE>
 static void emu_inv_w(const HostBehz &H, int j, const u64 *in, u64 *out)
 {
     using S = NttShape<LOGN, LOGE>;
     std::vector<u64> smem(S::SMEM_WORDS), tmp(in, in + S::N);
+    if constexpr (S::NPASS == 4)
+        for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 3>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
     for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 2>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
     for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 1>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
     for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 0>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
@@ -105,8 +109,8 @@ static int fwd_w_dispatch(const HostBehz &H, int j, const u64 *in, u64 *out)
     case 10: emu_fwd_w<10, 4>(H, j, in, out); return 0;
     case 11: emu_fwd_w<11, 4>(H, j, in, out); return 0;
     case 12: emu_fwd_w<12, 4>(H, j, in, out); return 0;
-    case 13: emu_fwd_w<13, 5>(H, j, in, out); return 0;
-    case 14: emu_fwd_w<14, 5>(H, j, in, out); return 0;
+    case 13: emu_fwd_w<13, FHE_LOGE13>(H, j, in, out); return 0;
+    case 14: emu_fwd_w<14, FHE_LOGE14>(H, j, in, out); return 0;
     default: return -1;
     }
 }
@@ -116,8 +120,8 @@ static int inv_w_dispatch(const HostBehz &H, int j, const u64 *in, u64 *out)
     case 10: emu_inv_w<10, 4>(H, j, in, out); return 0;
     case 11: emu_inv_w<11, 4>(H, j, in, out); return 0;
     case 12: emu_inv_w<12, 4>(H, j, in, out); return 0;
-    case 13: emu_inv_w<13, 5>(H, j, in, out); return 0;
-    case 14: emu_inv_w<14, 5>(H, j, in, out); return 0;
+    case 13: emu_inv_w<13, FHE_LOGE13>(H, j, in, out); return 0;
+    case 14: emu_inv_w<14, FHE_LOGE14>(H, j, in, out); return 0;
     default: return -1;
     }
 }
