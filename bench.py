@@ -244,7 +244,7 @@ def main():
         cs_t = torch.tensor([folded], dtype=torch.int64, device="cuda")
 
     # ---- side measurement (not the headline): the whole server_jpeg tile step, colour conversion
-    # fused into the forward NTT (fhe_jpeg_rgb_tiles), in place on the same resident buffer ------
+    # as an NTT-domain pass (fhe_jpeg_rgb_tiles), in place on the same resident buffer ------
     tile_info = None
     if not args.no_tile:
         jplan = pkg.JpegPlan(ctx, enc, pkg.YQT, pkg.UVQT)
