@@ -304,3 +304,40 @@ def test_device_block_cache(gpu, oracle_mod):
         ctx.free(c + 256)              # not a block of this allocator
     ctx.free(c)
     ctx.close()
+
+
+@pytest.mark.parametrize("n", [2048, 8192])
+def test_sparse_multiply_plain_random_terms(gpu, oracle_mod, n):
+    """The signed-rotation route of fhe_multiply_plain on random plaintexts with 1..8 coefficients in
+    {+1, -1} at random exponents (including 0 and n-1: every wrap-around case), sizes 2 and 3, against
+    the oracle's NTT-based multiply_plain; and 9 terms / a coefficient 2 take the dense route."""
+    ctx, o = make(gpu, oracle_mod, n)
+    t = int(ctx.t)
+    rng = np.random.default_rng(n)
+    plains = []
+    for terms in (1, 2, 3, 5, 8, 8, 9):
+        p = np.zeros(n, dtype=np.uint64)
+        exps = rng.choice(n, size=terms, replace=False)
+        exps[0] = [0, n - 1, 1, n // 2, n - 2, 7, 3][len(plains)]
+        for e in exps:
+            p[int(e)] = 1 if rng.integers(2) else t - 1
+        plains.append(p)
+    two = np.zeros(n, dtype=np.uint64)
+    two[5] = 2
+    plains.append(two)
+    tab = gpu.PlainTable(ctx, np.stack(plains))
+    for size in (2, 3):
+        n_ct, W = 3, ctx.ct_words(size)
+        a = o.fill_uniform(7, n_ct, size, 0x51DE)
+        da = ctx.to_device(a)
+        for i, p in enumerate(plains):
+            ctx.upload(da, a)
+            ctx.multiply_plain(da, n_ct, tab, i, size)
+            got = fetch(ctx, da, a.size)
+            ref = a.copy()
+            for c in range(n_ct):
+                o.multiply_plain(ref[c * W:(c + 1) * W], p, size)
+            assert (got == ref).all(), (size, i)
+        ctx.free(da)
+    tab.close()
+    ctx.close()
