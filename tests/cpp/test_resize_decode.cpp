@@ -1,7 +1,7 @@
 // test_resize_decode.cpp -- the C++ host layer for the resize and decode op libraries
 // (host/fhe_resize_b200.hpp, host/fhe_decode_b200.hpp) on a real B200.
 //
-// Usage: test_resize_decode <n> <in.bin> <out.bin>
+// Usage: test_resize_decode <n> <in.bin> <out.bin> [<evk.bin> <dbc> [<ncoeff> <fcoeff>]]
 // in.bin (raw u64, size-2 ciphertexts of W = 2*k*n words, written by tests/test_host_cpp.py from
 // the oracle's generator / encryptor):
 //   [0..4]   A B C D t            -> Cubic level 1 (size 4), Cubic level 2 on four copies (size 6),
@@ -70,7 +70,7 @@ int main(int argc, char **argv)
         } quiet;
 
         Evaluator evaluator(ctx);
-        FractionalEncoder encoder(ctx, 64, 32);
+        FractionalEncoder encoder(ctx, argc > 7 ? (uint32_t)std::atoi(argv[6]) : 64, argc > 7 ? (uint32_t)std::atoi(argv[7]) : 32);
         size_t next_zero = 8, next_frac = 16;
         Encryptor zeros([&](const Plaintext &, Ciphertext &dst) { dst = ct_at(next_zero++); });
         Encryptor fracs([&](const Plaintext &, Ciphertext &dst) { dst = ct_at(next_frac++); });
@@ -200,6 +200,20 @@ int main(int argc, char **argv)
             Cubic(cub2, Ar, Br, Cr, Dr, tr, evaluator, encoder, zeros);
             REQUIRE(cub2.size() == 2);
             dump(cub2);
+            // the whole step with every product relinearised, reference order and batched
+            {
+                next_zero = 8;
+                Ciphertext amp3 = ct_at(5), idx3 = ct_at(6), cnt3 = ct_at(7);
+                std::vector<Ciphertext> run3, run4;
+                approximated_step(amp3, idx3, cnt3, 8, 2, 0.25, 2, 1, run3, evaluator, encoder, zeros);
+                REQUIRE(run3.size() == 2 && run3[0].size() == 2 && next_zero == 16);
+                dump(run3[0]);
+                dump(run3[1]);
+                next_zero = 8;
+                Ciphertext amp4 = ct_at(5), idx4 = ct_at(6), cnt4 = ct_at(7);
+                approximated_step_batched(amp4, idx4, cnt4, 8, 2, 0.25, 2, 1, run4, evaluator, encoder, zeros);
+                REQUIRE(run4.size() == 2 && same(run3[0], run4[0]) && same(run3[1], run4[1]));
+            }
             // batched == single under the same policy
             CiphertextBatch xs(ctx, 2, 2), rs;
             xs.set(0, ct_at(0));

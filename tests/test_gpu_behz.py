@@ -31,6 +31,13 @@ CASES = [  # n, chain source, (size_a, size_b), n_ct
     (1024, 4096, (2, 2), 5),
     (2048, 2048, (2, 3), 2),
     (16384, 16384, (2, 2), 1),
+    # the products the decode graphs form at BASELINE config 5's parameters (k = 4; fhe_decode.h:67-97,
+    # 235, 239): x^8 * x, sin * cos, term * amplitude -- and the two largest of the bicubic graph
+    (8192, 8192, (9, 2), 2),
+    (8192, 8192, (11, 11), 1),
+    (8192, 8192, (21, 2), 1),
+    (8192, 8192, (4, 2), 3),
+    (8192, 8192, (5, 5), 1),
 ]
 
 
@@ -61,7 +68,7 @@ def test_multiply_vs_oracle(gpu, oracle_mod, n, chain, sizes, n_ct):
     ctx.close()
 
 
-@pytest.mark.parametrize("n,size,n_ct", [(4096, 2, 3), (4096, 3, 2), (8192, 2, 2), (4096, 5, 1)])
+@pytest.mark.parametrize("n,size,n_ct", [(4096, 2, 3), (4096, 3, 2), (8192, 2, 2), (4096, 5, 1), (8192, 3, 2), (8192, 5, 1)])
 def test_square_vs_oracle_and_multiply(gpu, oracle_mod, n, size, n_ct):
     q = oracle_mod.default_coeff_modulus(n)
     ctx, o = gpu.Context(n, q), oracle_mod.Oracle(n, q)

@@ -72,9 +72,10 @@ def resize_bicubic_oracle(o, src, ow, oh, dw, dh, fracs):
     return np.concatenate(out), nf
 
 
-def sin_relin_oracle(o, x, zero, evk, dbc):
-    """homomorphic_sin (fhe_decode.h:48-120) op by op on the oracle with every ct x ct product
-    relinearised to size 2 (host/seal_b200.hpp Evaluator::set_relinearization)."""
+def sincos_relin_oracle(o, x, zero, evk, dbc, sign):
+    """homomorphic_sin (sign +1, fhe_decode.h:48-120) / homomorphic_cos (sign -1, :128-200) op by op on the
+    oracle with every ct x ct product relinearised to size 2 (host/seal_b200.hpp
+    Evaluator::set_relinearization)."""
     import math
 
     def rl(c):
@@ -94,11 +95,50 @@ def sin_relin_oracle(o, x, zero, evk, dbc):
     p8 = sq(sq(sq(sh)))
     p10 = mul(mul(sq(sq(sq(sh))), sh), sh)
     res = zero.copy()
-    o.add_plain(res, o.encode(-1.0))
+    o.add_plain(res, o.encode(sign * -1.0))
     for term, coef in ((p2, 0.5), (p4, -1 / 24.0), (p6, 1 / 720.0), (p8, -1 / 40320.0), (p10, 1 / 3628800.0)):
-        o.multiply_plain(term, o.encode(coef))
+        o.multiply_plain(term, o.encode(sign * coef))
         o.add(res, term)
     return res
+
+
+def sin_relin_oracle(o, x, zero, evk, dbc):
+    return sincos_relin_oracle(o, x, zero, evk, dbc, 1.0)
+
+
+def approximated_step_relin_oracle(o, amplitude, index, count, order, degree, delta, npos, zeros, evk, dbc):
+    """approximated_step (fhe_decode.h:202-242) op by op -- `offset += encode(i)` inside the j loop and
+    the float casts included -- with every product relinearised; `zeros`: the fresh encryptions the
+    series start from, consumed sin then cos per (i, j)."""
+    import math
+    W = o.ct_words(2)
+    b = count.copy()
+    o.multiply_plain(b, o.encode(0.5))
+    offset = index.copy()
+    o.add(offset, b)
+    o.add_plain(offset, o.encode(-0.5))
+    o.negate(offset)
+    o.add_plain(b, o.encode(delta - 0.5))
+    run, nz = [], 0
+    for i in range(npos):
+        c = b.copy()
+        o.multiply_plain(c, o.encode(1.0 / float(order)))
+        for j in range(1, degree + 1):
+            arg_factor = float(np.float32(j)) * math.pi / float(order)
+            sin_arg = b.copy()
+            o.multiply_plain(sin_arg, o.encode(arg_factor))
+            cos_arg = offset.copy()
+            o.add_plain(offset, o.encode(float(i)))
+            o.multiply_plain(cos_arg, o.encode(arg_factor))
+            s = sincos_relin_oracle(o, sin_arg, zeros[nz * W:(nz + 1) * W], evk, dbc, 1.0)
+            cs = sincos_relin_oracle(o, cos_arg, zeros[(nz + 1) * W:(nz + 2) * W], evk, dbc, -1.0)
+            nz += 2
+            term = o.relinearize(o.multiply(s, 2, cs, 2), 3, evk, dbc, 1)
+            o.multiply_plain(term, o.encode(2.0 / (math.pi * float(np.float32(j)))))
+            o.add(c, term)
+        c = o.relinearize(o.multiply(c, 2, amplitude.copy(), 2), 3, evk, dbc, 1)
+        run.append(c)
+    return np.concatenate(run)
 
 
 def cubic_relin_oracle(o, A, B, C, D, t, evk, dbc):
@@ -145,10 +185,12 @@ def linear_relin_oracle(o, A, B, t, evk, dbc):
 
 
 @pytest.mark.gpu
-def test_resize_decode_host_layer_matches_oracle_on_gpu(pkg, oracle_mod, tmp_path):
+@pytest.mark.parametrize("n,ic,fc,dbc", [(2048, 64, 32, 16), (8192, 100, 100, 30)])
+def test_resize_decode_host_layer_matches_oracle_on_gpu(pkg, oracle_mod, tmp_path, n, ic, fc, dbc):
+    """n = 2048: one limb (k_behz_extend<1,1>); n = 8192: the parameters of BASELINE configs 3 and 5
+    (k = 4, FractionalEncoder(100, 100), dbc 30)"""
     exe = build_exe(pkg)
-    n = 2048
-    o = oracle_mod.Oracle(n, oracle_mod.default_coeff_modulus(n), 1 << 14, 64, 32)
+    o = oracle_mod.Oracle(n, oracle_mod.default_coeff_modulus(n), 1 << 14, ic, fc)
     W = o.ct_words(2)
     n_in = 34 + 90
     data = o.fill_uniform(0, n_in, 2, 0xD1CE)
@@ -160,10 +202,9 @@ def test_resize_decode_host_layer_matches_oracle_on_gpu(pkg, oracle_mod, tmp_pat
     data[4 * W:5 * W] = o.encrypt(pk, o.encode(0.625), 200)
     fin, fout, fkey = str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(tmp_path / "evk.bin")
     data.tofile(fin)
-    dbc = 16
     evk = o.evk_gen(sk, dbc, 1, 77)
     evk.tofile(fkey)
-    r = subprocess.run([exe, str(n), fin, fout, fkey, str(dbc)], capture_output=True, text=True, timeout=900)
+    r = subprocess.run([exe, str(n), fin, fout, fkey, str(dbc), str(ic), str(fc)], capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.startswith("PASS")
     got = np.fromfile(fout, dtype=np.uint64)
@@ -192,16 +233,22 @@ def test_resize_decode_host_layer_matches_oracle_on_gpu(pkg, oracle_mod, tmp_pat
     tz = np.zeros(W, dtype=np.uint64)
     o.add_plain(tz, o.encode(0.375))
     want.append(tz)
-    # Evaluator::set_relinearization: the same graphs with every product relinearised (dbc 16)
+    # Evaluator::set_relinearization: the same graphs with every product relinearised
     s_rl = sin_relin_oracle(o, ct(0), ct(8), evk, dbc)
     lin_rl = linear_relin_oracle(o, ct(0), ct(1), ct(4), evk, dbc)
     cub_rl = cubic_relin_oracle(o, ct(0), ct(1), ct(2), ct(3), ct(4), evk, dbc)
-    want += [s_rl, lin_rl, cub_rl]
+    step_rl = approximated_step_relin_oracle(o, ct(5), ct(6), ct(7), 8, 2, 0.25, 2, data[8 * W:16 * W].copy(), evk, dbc)
+    want += [s_rl, lin_rl, cub_rl, step_rl]
     want = np.concatenate(want)
     assert got.size == want.size
     assert (got == want).all()
-    # one multiplicative level fits the single 54-bit prime: (1 - t) A + t B = 0.375 * 12 + 0.625 * 200
+    # (1 - t) A + t B = 0.375 * 12 + 0.625 * 200
     assert abs(o.decode(o.decrypt(sk, lin_rl, 2)) - 129.5) < 1e-6
-    # (what the Cubic decrypts to is checked in tests/test_oracle_behz.py with a two-prime modulus;
-    # coeff_modulus_128(2048) is one 54-bit prime, too small for two multiplicative levels)
+    if n == 8192:
+        # four limbs carry both multiplicative levels of Cubic: the size-4 level-1 result decrypts to
+        # ((a + b) t^2 + c t) / 2 + B of the plaintext mirror (t3 = t * t, fhe_resize.h:175)
+        A, B, C, D, t = 12.0, 200.0, 131.0, 77.0, 0.625
+        a, b, cc = -A + 3 * B - 3 * C + D, 2 * A - 5 * B + 4 * C - D, C - A
+        assert abs(o.decode(o.decrypt(sk, c1, 4)) - ((a * t * t + b * t * t + cc * t) * 0.5 + B)) < 1e-6
+        assert abs(o.decode(o.decrypt(sk, cub_rl, 2)) - ((a * t * t + b * t * t + cc * t) * 0.5 + B)) < 1e-6
     assert abs(o.decode(o.decrypt(sk, tz, 2)) - 0.375) < 1e-9

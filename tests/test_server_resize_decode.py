@@ -171,3 +171,37 @@ def test_published_bilinear_rms_error_through_the_encrypted_pipeline(pkg, oracle
     assert len(got) == dw * dh * 3 and all(g.size == o.ct_words(4) for g in got)
     values = np.array([o.decode(o.decrypt(sk, ct, 4)) for ct in got]).reshape(dh, dw, 3)
     assert reference_rms(client_pixels(values), lin) == r["published_rms_error_bilinear"]
+
+
+@pytest.mark.gpu
+def test_published_bicubic_rms_error_through_the_encrypted_pipeline(pkg, oracle_mod, tmp_path):
+    """The bicubic sweep of benchmark/results.txt:22-26 at n = 8192, t = 2^14 (the default plain modulus
+    needs four limbs for the two multiplicative levels of Cubic): image/boazbarak.jpg -> every sample
+    encrypted (oracle harness) -> server_resize_b200 --bicubic (17 x 17) on the GPU -> decryption of the
+    size-6 results -> int(decode), CLAMP -> RMSError against OpenCV's INTER_LINEAR picture, which is
+    what the reference's benchmark compares with (benchmark.py:24-31 never passes --bicubic to the
+    receiving client, client_resize.cpp:17,215, fhe_resize.h:51-52): 19.8048."""
+    from test_resize_published import client_pixels, fixtures, reference_rms
+    exe = resize_exe(pkg)
+    img, lin, _, r = fixtures()
+    oh, ow, _ = img.shape
+    dw, dh = r["width"], r["height"]
+    n = 8192
+    o = oracle_mod.Oracle(n, oracle_mod.default_coeff_modulus(n), 1 << 14)
+    k = o.k
+    assert k == 4
+    sk, pk = o.keygen(19)
+    os.makedirs(tmp_path / "keys")
+    os.makedirs(tmp_path / "image")
+    (tmp_path / "keys" / "params.txt").write_text(f"{ow} {oh} 3 16384\n")
+    with open(tmp_path / "image" / "nothingpersonnel.txt", "wb") as f:      # client_resize --send: RGB interleaved, row major
+        for i, v in enumerate(img.reshape(-1)):
+            wire_save(f, o.encrypt(pk, o.encode(float(v)), i + 1), 2, k, n)
+    res = subprocess.run([exe, "--bicubic", "-w", str(dw), "-h", str(dh), "--cmod", str(n)], capture_output=True, text=True,
+                         cwd=tmp_path, timeout=2400)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    got = wire_load_all(tmp_path / "image" / "zoop.txt", k, n)
+    assert len(got) == dw * dh * 3 and all(g.size == o.ct_words(6) for g in got)
+    os.remove(tmp_path / "image" / "nothingpersonnel.txt")
+    values = np.array([o.decode(o.decrypt(sk, ct, 6)) for ct in got]).reshape(dh, dw, 3)
+    assert reference_rms(client_pixels(values), lin) == r["published_rms_error_bicubic"]
