@@ -28,6 +28,7 @@ struct BehzDev {
     uint32_t n, logn, k, kb, nb;
     u64 q[BEHZ_MAXK], qr0[BEHZ_MAXK], qr1[BEHZ_MAXK];       // primes of q and floor(2^128 / q_i)
     u64 b[BEHZ_MAXB], br0[BEHZ_MAXB], br1[BEHZ_MAXB];       // B_sk
+    u32 bd8[BEHZ_MAXB];                   // 8 (2^61 - b_j) = 2^64 mod b_j: the auxiliary primes are 2^61 - delta, delta < 2^26
     // extension q -> B_sk (fastbconv_mtilde + mont_rq)
     W2 mt_qhat_inv[BEHZ_MAXK];            // m~ (q/q_i)^-1 mod q_i         {w, floor(w 2^64 / q_i)}
     u32 qhat_mod_mt[BEHZ_MAXK];           // (q/q_i) mod 2^32
@@ -51,6 +52,23 @@ struct WideRing {
 };
 
 FHE_HD u64 barrett_u128(u128d z, u64 q, u64 r0, u64 r1) { return barrett128((u64)z, (u64)(z >> 64), q, r0, r1); }
+// z mod p, canonical, for p = 2^61 - delta and ANY z < 2^128; d8 = 8 delta = 2^64 mod p (< 2^29).
+// Two folds of the high part (2^64 = d8) and one of the top three bits (2^61 = delta): three
+// 32-bit-operand multiplications instead of the five 64 x 64 products of a Barrett 128 -> 64 step.
+// Every auxiliary prime of the BEHZ base has this shape (behz_host.hpp kAuxSmallMods, kMsk).
+FHE_HD u64 fold61(u128d z, u64 p, u32 d8)
+{
+    const u64 z0 = (u64)z, z1 = (u64)(z >> 64);
+    const u64 lo = (u64)(u32)z1 * d8, hi = (z1 >> 32) * d8;     // z1 * d8 = lo + hi 2^32 (< 2^93)
+    const u64 t0 = lo + (hi << 32);
+    u64 t1 = (hi >> 32) + (t0 < lo);
+    const u64 w0 = z0 + t0;                                       // z = w0 + t1 2^64 (mod p), t1 < 2^30
+    t1 += (w0 < z0);
+    u64 s = w0 + t1 * d8;                                         // t1 * d8 < 2^59
+    if (s < w0) s += d8;                                          // wrapped once more; now small
+    const u64 r = (s & 0x1fffffffffffffffull) + (s >> 61) * (u64)(d8 >> 3);   // < 2^61 + 2^29 < 2p
+    return csub(r, p);
+}
 // x * c mod q, canonical, c a Shoup pair scaled by 2^64
 FHE_HD u64 mulsh_canon(u64 x, W2 c, u64 q) { return csub(mulsh(x, c, q), q); }
 
@@ -86,7 +104,7 @@ FHE_HD void behz_extend_coeff_t(const BehzDev &B, const u64 *x, size_t xs, u64 *
 #pragma unroll
             for (int i = 0; i < MK; ++i)
                 if (ST || i < k) acc += (u128d)y[i] * B.C[j][i];
-            out[j * os] = barrett_u128(acc, B.b[j], B.br0[j], B.br1[j]);
+            out[j * os] = fold61(acc, B.b[j], B.bd8[j]);
         }
 }
 
@@ -109,7 +127,7 @@ FHE_HD void behz_scale_coeff_t(const BehzDev &B, const u64 *xq, size_t qs, const
 #pragma unroll
             for (int i = 0; i < MK; ++i)
                 if (ST || i < k) acc += (u128d)y[i] * B.F[j][i];
-            f[j] = barrett_u128(acc, B.b[j], B.br0[j], B.br1[j]);
+            f[j] = fold61(acc, B.b[j], B.bd8[j]);
         }
     // fastbconv_sk: alpha = [(conv_B->msk(f) - f_sk) B^-1] mod m_sk, centred
     u64 fsk = 0;
@@ -124,7 +142,7 @@ FHE_HD void behz_scale_coeff_t(const BehzDev &B, const u64 *xq, size_t qs, const
             acc += (u128d)z[l] * B.G[l];
         }
     const u64 msk = B.b[kb];
-    const u64 alpha = barrett_u128(acc, msk, B.br0[kb], B.br1[kb]);
+    const u64 alpha = fold61(acc, msk, B.bd8[kb]);
     const bool neg = alpha > (msk >> 1);
     const u64 aabs = neg ? msk - alpha : alpha;
 #pragma unroll

@@ -86,6 +86,8 @@ inline bool build_behz(const HostRing &R, HostBehz &H, std::string &err)
         D.b[j] = p;
         const u128 ratio = (~(u128)0) / p;
         D.br0[j] = (u64)ratio; D.br1[j] = (u64)(ratio >> 64);
+        if (p >= (1ull << 61) || (1ull << 61) - p >= (1ull << 26)) { err = "auxiliary prime is not 2^61 - delta with delta < 2^26"; return false; }
+        D.bd8[j] = (u32)(8 * ((1ull << 61) - p));
         const u64 inv_mt = h_invmod(MT % p, p);
         const u64 q_mod = h_prod_except(q, none, p), q_inv = h_invmod(q_mod, p);
         const u64 dpos = h_mulmod(q_mod, inv_mt, p);

@@ -76,14 +76,13 @@ FHE_HD void inv_stage(u64 *v, int tau, const W2 *__restrict__ itw, const LimbWid
 
 }  // namespace nttwide
 
-// forward pass P: inputs in [0, 4q) (canonical on the first pass); last pass stores canonical values
+// forward pass P on a register file: inputs in [0, 4q) (canonical on the first pass); the last pass
+// leaves canonical values
 template <int LOGN, int LOGE, int P>
-FHE_HD void nttw_fwd_pass(int tau, const u64 *gin, u64 *gout, u64 *smem, const W2 *tw, const LimbWide &L)
+FHE_HD void nttw_fwd_compute(u64 *v, int tau, const W2 *tw, const LimbWide &L)
 {
     using S = NttShape<LOGN, LOGE>;
     constexpr int R = nttdetail::PassGeom<LOGN, LOGE, P>::R;
-    u64 v[S::E];
-    ntt_fwd_load<LOGN, LOGE, P>(v, tau, gin, smem);
     nttwide::fwd_stage<LOGN, LOGE, P, 0>(v, tau, tw, L);
     if constexpr (R > 1) nttwide::fwd_stage<LOGN, LOGE, P, 1>(v, tau, tw, L);
     if constexpr (R > 2) nttwide::fwd_stage<LOGN, LOGE, P, 2>(v, tau, tw, L);
@@ -93,16 +92,22 @@ FHE_HD void nttw_fwd_pass(int tau, const u64 *gin, u64 *gout, u64 *smem, const W
 #pragma unroll
         for (int e = 0; e < S::E; ++e) v[e] = csub(csub(v[e], L.q2), L.q);
     }
+}
+template <int LOGN, int LOGE, int P>
+FHE_HD void nttw_fwd_pass(int tau, const u64 *gin, u64 *gout, u64 *smem, const W2 *tw, const LimbWide &L)
+{
+    u64 v[NttShape<LOGN, LOGE>::E];
+    ntt_fwd_load<LOGN, LOGE, P>(v, tau, gin, smem);
+    nttw_fwd_compute<LOGN, LOGE, P>(v, tau, tw, L);
     ntt_fwd_store<LOGN, LOGE, P>(v, tau, gout, smem);
 }
-// inverse pass P (P = NPASS-1 first): inputs in [0, 2q); P == 0 stores canonical values times n^-1
+// inverse pass P (P = NPASS-1 first) on a register file: inputs in [0, 2q); P == 0 leaves canonical
+// values times n^-1
 template <int LOGN, int LOGE, int P>
-FHE_HD void nttw_inv_pass(int tau, const u64 *gin, u64 *gout, u64 *smem, const W2 *itw, const LimbWide &L)
+FHE_HD void nttw_inv_compute(u64 *v, int tau, const W2 *itw, const LimbWide &L)
 {
     using S = NttShape<LOGN, LOGE>;
     constexpr int R = nttdetail::PassGeom<LOGN, LOGE, P>::R;
-    u64 v[S::E];
-    ntt_inv_load<LOGN, LOGE, P>(v, tau, gin, smem);
     nttwide::inv_stage<LOGN, LOGE, P, 0>(v, tau, itw, L);
     if constexpr (R > 1) nttwide::inv_stage<LOGN, LOGE, P, 1>(v, tau, itw, L);
     if constexpr (R > 2) nttwide::inv_stage<LOGN, LOGE, P, 2>(v, tau, itw, L);
@@ -112,5 +117,35 @@ FHE_HD void nttw_inv_pass(int tau, const u64 *gin, u64 *gout, u64 *smem, const W
 #pragma unroll
         for (int e = 0; e < S::E; ++e) v[e] = csub(v[e], L.q);
     }
+}
+template <int LOGN, int LOGE, int P>
+FHE_HD void nttw_inv_pass(int tau, const u64 *gin, u64 *gout, u64 *smem, const W2 *itw, const LimbWide &L)
+{
+    u64 v[NttShape<LOGN, LOGE>::E];
+    ntt_inv_load<LOGN, LOGE, P>(v, tau, gin, smem);
+    nttw_inv_compute<LOGN, LOGE, P>(v, tau, itw, L);
     ntt_inv_store<LOGN, LOGE, P>(v, tau, gout, smem);
 }
+
+#if defined(__CUDACC__)
+// pass chains, as in ntt.cuh: forward passes P .. PEND-1 with a barrier after each; inverse passes P
+// down to PEND with a barrier before each
+template <int LOGN, int LOGE, int P, int PEND>
+__device__ __forceinline__ void nttw_fwd_passes(int tau, const u64 *gin, u64 *gout, u64 *smem, const W2 *tw, const LimbWide &L)
+{
+    if constexpr (P < PEND) {
+        nttw_fwd_pass<LOGN, LOGE, P>(tau, gin, gout, smem, tw, L);
+        __syncthreads();
+        nttw_fwd_passes<LOGN, LOGE, P + 1, PEND>(tau, gin, gout, smem, tw, L);
+    }
+}
+template <int LOGN, int LOGE, int P, int PEND>
+__device__ __forceinline__ void nttw_inv_passes(int tau, const u64 *gin, u64 *gout, u64 *smem, const W2 *itw, const LimbWide &L)
+{
+    if constexpr (P >= PEND) {
+        __syncthreads();
+        nttw_inv_pass<LOGN, LOGE, P>(tau, gin, gout, smem, itw, L);
+        nttw_inv_passes<LOGN, LOGE, P - 1, PEND>(tau, gin, gout, smem, itw, L);
+    }
+}
+#endif

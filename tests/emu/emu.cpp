@@ -186,6 +186,12 @@ int emu_multiply(void *ring, void *h, const uint64_t *a1, uint32_t s1, const uin
     return 0;
 }
 
+// z = z1 2^64 + z0 mod p (p = 2^61 - delta), the special-prime reduction of csrc/behz.cuh
+uint64_t emu_fold61(uint64_t z0, uint64_t z1, uint64_t p)
+{
+    return fold61(((u128d)z1 << 64) | z0, p, (u32)(8 * ((1ull << 61) - p)));
+}
+
 void *emu_ring_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, char *err, int errlen)
 {
     auto R = std::make_unique<HostRing>();

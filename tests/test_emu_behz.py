@@ -95,3 +95,18 @@ def test_extend_scale_and_multiply_bodies_match_oracle(E, oracle_mod, n, chain):
         assert (want == out).all(), (n, chain, s1, s2)
     E.emu_behz_destroy(h)
     E.emu_ring_destroy(r)
+
+
+def test_fold61_is_exact_for_any_128_bit_value(E):
+    """fold61 (csrc/behz.cuh): z mod p for the auxiliary primes p = 2^61 - delta, any z < 2^128"""
+    E.emu_fold61.restype = C.c_uint64
+    E.emu_fold61.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+    primes = [0x1fffffffffe00001, 0x1fffffffffb40001, 0x1ffffffffe780001, 0x1ffffffffe4c0001]
+    rng = np.random.default_rng(61)
+    M = (1 << 64) - 1
+    for p in primes:
+        zs = [0, 1, p - 1, p, p + 1, 2 * p, (1 << 128) - 1, (1 << 127), M, M << 64, (p << 64) | (p - 1), ((1 << 61) - 1) << 64 | M]
+        zs += [int(a) << 64 | int(b) for a, b in rng.integers(0, 1 << 63, (400, 2), dtype=np.uint64) * 2 + 1]
+        zs += [(k * p - 1) % (1 << 128) for k in (1 << 64, (1 << 66) + 12345, (1 << 67) - 1)]
+        for z in zs:
+            assert E.emu_fold61(z & M, z >> 64, p) == z % p, (hex(p), hex(z))
