@@ -46,8 +46,8 @@ def build(force: bool = False) -> str:
     """Compile csrc/ for sm_100a into the in-tree libfhe_b200.so (nvcc cross-compiles without a GPU)."""
     src = os.path.join(_HERE, "csrc", "fhe_b200.cu")
     deps = [src] + [os.path.join(_HERE, "csrc", f) for f in (
-        "ntt.cuh", "dct.cuh", "modarith.cuh", "ring_host.hpp", "ntt_wide.cuh", "behz.cuh", "behz_host.hpp", "behz_api.inc",
-        "jpeg_api.inc")]
+        "ntt.cuh", "dct.cuh", "modarith.cuh", "ring_host.hpp", "behz.cuh", "behz_host.hpp", "behz_api.inc",
+        "resize_api.inc", "jpeg_api.inc")]
     deps.append(os.path.join(ROOT, "include", "fhe_b200.h"))
     stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
     if force or stale:
@@ -112,6 +112,13 @@ def lib():
         "fhe_ntt_loge": (u32, [u32]),
         "fhe_multiply": (i32, [vp, vp, u32, vp, u32, vp, u64]),
         "fhe_square": (i32, [vp, vp, u32, vp, u64]),
+        "fhe_form_create": (i32, [vp, vp, u32, u64, C.POINTER(vp)]),
+        "fhe_form_destroy": (None, [vp]),
+        "fhe_multiply_form": (i32, [vp, vp, u32, vp, u32, vp, u64]),
+        "fhe_resize_plan_create": (i32, [vp, u64p, C.POINTER(vp)]),
+        "fhe_resize_plan_destroy": (None, [vp]),
+        "fhe_cubic": (i32, [vp, vp, C.POINTER(vp), u32, vp, vp, vp, u32, vp, u64]),
+        "fhe_linear": (i32, [vp, C.POINTER(vp), u32, vp, vp, u32, vp, u64]),
         "fhe_evk_digits": (u32, [vp, u32]),
         "fhe_evk_create": (i32, [vp, u64p, u32, u32, C.POINTER(vp)]),
         "fhe_evk_destroy": (None, [vp]),
@@ -132,7 +139,7 @@ EXPORTED_SYMBOLS = (
     "fhe_ntt_forward", "fhe_ntt_inverse", "fhe_dct_plan_create", "fhe_dct_plan_destroy",
     "fhe_dct8x8_quantize", "fhe_dct8x8_quantize_host", "fhe_fill_uniform", "fhe_checksum",
     "fhe_launch_count", "fhe_set_dct_chunk_blocks", "fhe_set_stage_timing", "fhe_get_stage_times",
-    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_encrypt_transparent", "fhe_ntt_loge", "fhe_multiply", "fhe_square", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
+    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_encrypt_transparent", "fhe_ntt_loge", "fhe_multiply", "fhe_square", "fhe_form_create", "fhe_form_destroy", "fhe_multiply_form", "fhe_resize_plan_create", "fhe_resize_plan_destroy", "fhe_cubic", "fhe_linear", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
 )
 
 
@@ -236,6 +243,24 @@ class Context:
     def square(self, a, size_a, dest, n_ct=1):
         _check(lib().fhe_square(self.h, C.c_void_p(a), size_a, C.c_void_p(dest), n_ct))
 
+    def form(self, a, size, n_ct=1) -> "OperandForm":
+        """the operand half of Evaluator::multiply, done once: BEHZ extension + forward NTTs (fhe_form_create)"""
+        return OperandForm(self, a, size, n_ct)
+
+    def multiply_form(self, fa: "OperandForm", a_div, fb: "OperandForm", b_div, dest, n_ct):
+        """product i = ciphertext i // a_div of fa times ciphertext i // b_div of fb -> dest (fhe_multiply_form)"""
+        _check(lib().fhe_multiply_form(self.h, fa.h, a_div, fb.h, b_div, C.c_void_p(dest), n_ct))
+
+    def cubic(self, plan: "ResizePlan", taps, size_in, ft, ft2, ft3, t_div, dest, n_ct):
+        """fused Cubic (fhe_resize.h:143-189) of n_ct calls; taps: n_ct * 4 device pointers (A B C D per call)"""
+        arr = (C.c_void_p * (4 * n_ct))(*[int(p) for p in taps])
+        _check(lib().fhe_cubic(self.h, plan.h, arr, size_in, ft.h, ft2.h, ft3.h, t_div, C.c_void_p(dest), n_ct))
+
+    def linear(self, taps, size_in, f1mt, ft, t_div, dest, n_ct):
+        """fused Linear (fhe_resize.h:191-204) of n_ct calls; taps: n_ct * 2 device pointers (A B per call)"""
+        arr = (C.c_void_p * (2 * n_ct))(*[int(p) for p in taps])
+        _check(lib().fhe_linear(self.h, arr, size_in, f1mt.h, ft.h, t_div, C.c_void_p(dest), n_ct))
+
     def evk_digits(self, dbc: int) -> int: return int(lib().fhe_evk_digits(self.h, dbc))
 
     def relinearize(self, a, size, evk: "EvaluationKeys", dest, n_ct=1):
@@ -294,6 +319,35 @@ class PlainTable:
             self.close()
         except Exception:
             pass
+
+
+class ResizePlan:
+    """fhe_resize_plan: the five plaintexts of Cubic from the caller's encoder (fhe_resize.h:151-183)."""
+
+    def __init__(self, ctx: "Context", enc: "FractionalEncoder"):
+        import numpy as np
+        plains = np.ascontiguousarray(np.stack([enc.encode(v) for v in (3.0, 2.0, 5.0, 4.0, 0.5)]), dtype=np.uint64)
+        self.h = C.c_void_p()
+        _check(lib().fhe_resize_plan_create(ctx.h, plains.ctypes.data_as(u64p), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().fhe_resize_plan_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class OperandForm:
+    """fhe_form: n_ct ciphertexts of `size` polynomials in the NTT domain of q and B_sk (include/fhe_b200.h)."""
+
+    def __init__(self, ctx: "Context", a, size: int, n_ct: int = 1):
+        self.h = C.c_void_p()
+        self.size, self.n_ct = size, n_ct
+        _check(lib().fhe_form_create(ctx.h, C.c_void_p(a), size, n_ct, C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().fhe_form_destroy(self.h)
+            self.h = C.c_void_p()
 
 
 class EvaluationKeys:

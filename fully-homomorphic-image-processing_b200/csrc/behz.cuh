@@ -13,9 +13,20 @@
 // the two per-coefficient kernels then is: k (or |B|) multiplications by a constant, and one
 // 128-bit multiply-accumulate row with a single Barrett reduction per output residue.
 //
+// The auxiliary base.  SEAL uses its 61-bit internal primes for B_sk.  The RESULT of the procedure does
+// not depend on that choice: the extension yields the residues of one integer X' = (S + q r) / m~
+// fixed by the q-residues alone, fast_floor the residues of one integer W = (t P - S') / q, and the
+// Shenoy-Kumaresan step returns W mod q exactly as long as |W| < B m_sk / 2 -- any base that is large
+// enough gives the same bits (tests/test_oracle_behz.py checks the big-int model with both bases;
+// every GPU parity test compares this base against the oracle's SEAL base).  So this library takes
+// its auxiliary primes just below 2^55, where the lazy arithmetic of ntt.cuh applies: the B_sk limbs
+// run the same butterflies, kernels and tables as the q limbs (no 61-bit transform at all), and the
+// primes have the shape 2^55 - delta (delta < 2^26), which turns every 128 -> 64-bit reduction modulo
+// them into three small multiplications (fold_aux).
+//
 // Data layout: a polynomial in base q is [k][n]; in base B_sk = B u {m_sk} it is [nb][n], m_sk last.
 #pragma once
-#include "ntt_wide.cuh"
+#include "ntt.cuh"
 
 namespace fhe {
 
@@ -28,7 +39,7 @@ struct BehzDev {
     uint32_t n, logn, k, kb, nb;
     u64 q[BEHZ_MAXK], qr0[BEHZ_MAXK], qr1[BEHZ_MAXK];       // primes of q and floor(2^128 / q_i)
     u64 b[BEHZ_MAXB], br0[BEHZ_MAXB], br1[BEHZ_MAXB];       // B_sk
-    u32 bd8[BEHZ_MAXB];                   // 8 (2^61 - b_j) = 2^64 mod b_j: the auxiliary primes are 2^61 - delta, delta < 2^26
+    u32 bdelta[BEHZ_MAXB];                // 2^55 - b_j (< 2^26): the auxiliary primes are 2^55 - delta
     // extension q -> B_sk (fastbconv_mtilde + mont_rq)
     W2 mt_qhat_inv[BEHZ_MAXK];            // m~ (q/q_i)^-1 mod q_i         {w, floor(w 2^64 / q_i)}
     u32 qhat_mod_mt[BEHZ_MAXK];           // (q/q_i) mod 2^32
@@ -45,28 +56,22 @@ struct BehzDev {
     u64 Bq_pos[BEHZ_MAXK], Bq_neg[BEHZ_MAXK];  // +- B mod q_i
 };
 
-struct WideRing {
-    uint32_t nb;
-    LimbWide limb[BEHZ_MAXB];
-    const W2 *tw, *itw;  // [nb][n], per-pass layout
-};
-
 FHE_HD u64 barrett_u128(u128d z, u64 q, u64 r0, u64 r1) { return barrett128((u64)z, (u64)(z >> 64), q, r0, r1); }
-// z mod p, canonical, for p = 2^61 - delta and ANY z < 2^128; d8 = 8 delta = 2^64 mod p (< 2^29).
-// Two folds of the high part (2^64 = d8) and one of the top three bits (2^61 = delta): three
-// 32-bit-operand multiplications instead of the five 64 x 64 products of a Barrett 128 -> 64 step.
-// Every auxiliary prime of the BEHZ base has this shape (behz_host.hpp kAuxSmallMods, kMsk).
-FHE_HD u64 fold61(u128d z, u64 p, u32 d8)
+// x * c.w mod q in [0, 2q) for any x < 2^64, c = {w, floor(w 2^64 / q)} (Shoup's exact quotient)
+FHE_HD u64 mulsh(u64 x, W2 c, u64 q) { return x * c.w - mulhi_u64(x, c.p) * q; }
+// z mod p, canonical, for an auxiliary prime p = 2^55 - delta (delta < 2^26) and z < 2^119 (every
+// accumulator here is a sum of at most 33 products of two values below 2^55 and 2^55: < 2^116).
+// Three folds of the part above bit 55 (2^55 = delta mod p): 64 x 26, 36 x 26 and 8 x 26-bit products
+// instead of the five 64 x 64 products of a Barrett 128 -> 64 step.
+FHE_HD u64 fold_aux(u128d z, u64 p, u32 delta)
 {
-    const u64 z0 = (u64)z, z1 = (u64)(z >> 64);
-    const u64 lo = (u64)(u32)z1 * d8, hi = (z1 >> 32) * d8;     // z1 * d8 = lo + hi 2^32 (< 2^93)
-    const u64 t0 = lo + (hi << 32);
-    u64 t1 = (hi >> 32) + (t0 < lo);
-    const u64 w0 = z0 + t0;                                       // z = w0 + t1 2^64 (mod p), t1 < 2^30
-    t1 += (w0 < z0);
-    u64 s = w0 + t1 * d8;                                         // t1 * d8 < 2^59
-    if (s < w0) s += d8;                                          // wrapped once more; now small
-    const u64 r = (s & 0x1fffffffffffffffull) + (s >> 61) * (u64)(d8 >> 3);   // < 2^61 + 2^29 < 2p
+    const u64 M55 = (1ull << 55) - 1;
+    const u64 zl = (u64)z & M55, zh = (u64)(z >> 55);                 // zh < 2^64
+    const u64 lo = (u64)(u32)zh * delta, hi = (zh >> 32) * delta;       // zh delta = lo + hi 2^32 (< 2^90)
+    const u128d w = (u128d)zl + lo + ((u128d)hi << 32);                 // < 2^91
+    const u64 wl = (u64)w & M55, wh = (u64)(w >> 55);                   // wh < 2^36
+    const u64 s = wl + wh * delta;                                       // < 2^55 + 2^62
+    const u64 r = (s & M55) + (s >> 55) * delta;                         // < 2^55 + 2^34 < 2p
     return csub(r, p);
 }
 // x * c mod q, canonical, c a Shoup pair scaled by 2^64
@@ -104,7 +109,7 @@ FHE_HD void behz_extend_coeff_t(const BehzDev &B, const u64 *x, size_t xs, u64 *
 #pragma unroll
             for (int i = 0; i < MK; ++i)
                 if (ST || i < k) acc += (u128d)y[i] * B.C[j][i];
-            out[j * os] = fold61(acc, B.b[j], B.bd8[j]);
+            out[j * os] = fold_aux(acc, B.b[j], B.bdelta[j]);
         }
 }
 
@@ -127,7 +132,7 @@ FHE_HD void behz_scale_coeff_t(const BehzDev &B, const u64 *xq, size_t qs, const
 #pragma unroll
             for (int i = 0; i < MK; ++i)
                 if (ST || i < k) acc += (u128d)y[i] * B.F[j][i];
-            f[j] = fold61(acc, B.b[j], B.bd8[j]);
+            f[j] = fold_aux(acc, B.b[j], B.bdelta[j]);
         }
     // fastbconv_sk: alpha = [(conv_B->msk(f) - f_sk) B^-1] mod m_sk, centred
     u64 fsk = 0;
@@ -142,7 +147,7 @@ FHE_HD void behz_scale_coeff_t(const BehzDev &B, const u64 *xq, size_t qs, const
             acc += (u128d)z[l] * B.G[l];
         }
     const u64 msk = B.b[kb];
-    const u64 alpha = fold61(acc, msk, B.bd8[kb]);
+    const u64 alpha = fold_aux(acc, msk, B.bdelta[kb]);
     const bool neg = alpha > (msk >> 1);
     const u64 aabs = neg ? msk - alpha : alpha;
 #pragma unroll
@@ -185,9 +190,9 @@ FHE_HD void behz_tensor_elem(const u64 *a, const u64 *b, u64 *d, size_t stride, 
 // ---------------------------------------------------------------------------------------------
 // The constants travel as a __grid_constant__ kernel parameter (3.3 KB): every read is a uniform
 // constant-bank access instead of a global load.
-// polys: [npoly][k][n] -> ext: [npoly][nb][n]
+// polys x: k limbs of n, `xs` words from one polynomial to the next -> ext: nb limbs of n, `es` words apart
 template <int K, int KB>
-__global__ void __launch_bounds__(256) k_behz_extend(const u64 *__restrict__ x, u64 *__restrict__ ext,
+__global__ void __launch_bounds__(256) k_behz_extend(const u64 *__restrict__ x, size_t xs, u64 *__restrict__ ext, size_t es,
                                                       unsigned long long npoly, const __grid_constant__ BehzDev B)
 {
     const unsigned long long total = npoly << B.logn;
@@ -195,12 +200,12 @@ __global__ void __launch_bounds__(256) k_behz_extend(const u64 *__restrict__ x, 
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long p = i >> B.logn;
         const uint32_t c = (uint32_t)(i & (B.n - 1));
-        behz_extend_coeff_t<K, KB>(B, x + p * B.k * B.n + c, B.n, ext + p * B.nb * B.n + c, B.n);
+        behz_extend_coeff_t<K, KB>(B, x + p * xs + c, B.n, ext + p * es + c, B.n);
     }
 }
-// dq: [npoly][k][n], db: [npoly][nb][n] -> out: [npoly][k][n]
+// dq: k limbs per polynomial (`qs` words apart), db: nb limbs per polynomial (`bs` apart) -> out: [npoly][k][n]
 template <int K, int KB>
-__global__ void __launch_bounds__(256) k_behz_scale(const u64 *__restrict__ dq, const u64 *__restrict__ db,
+__global__ void __launch_bounds__(256) k_behz_scale(const u64 *__restrict__ dq, size_t qs, const u64 *__restrict__ db, size_t bs,
                                                      u64 *__restrict__ out, unsigned long long npoly,
                                                      const __grid_constant__ BehzDev B)
 {
@@ -209,78 +214,10 @@ __global__ void __launch_bounds__(256) k_behz_scale(const u64 *__restrict__ dq, 
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long p = i >> B.logn;
         const uint32_t c = (uint32_t)(i & (B.n - 1));
-        behz_scale_coeff_t<K, KB>(B, dq + p * B.k * B.n + c, B.n, db + p * B.nb * B.n + c, B.n, out + p * B.k * B.n + c, B.n);
+        behz_scale_coeff_t<K, KB>(B, dq + p * qs + c, B.n, db + p * bs + c, B.n, out + p * B.k * B.n + c, B.n);
     }
 }
 
-// Tensor product in the NTT domain, one modulus set (nl limbs): for every ciphertext pair and
-// every output poly l:  D[l] = sum_{x + y = l} A[x] (.) B[y]  per limb and position, 128-bit
-// accumulation, one Barrett reduction.  A: [n_ct][s1][nl][n], Bm: [n_ct][s2][nl][n] (may be A),
-// D: [n_ct][s1 + s2 - 1][nl][n].  mod / r0 / r1: [nl].
-__global__ void __launch_bounds__(256) k_behz_tensor(const u64 *__restrict__ A, const u64 *__restrict__ Bm,
-                                                      u64 *__restrict__ D, uint32_t s1, uint32_t s2, uint32_t nl,
-                                                      uint32_t logn, unsigned long long n_ct,
-                                                      const u64 *__restrict__ mod, const u64 *__restrict__ r0,
-                                                      const u64 *__restrict__ r1)
-{
-    // grid = (nl * n / 256, ciphertexts (strided)): r = limb * n + pos without a 64-bit division
-    const uint32_t sd = s1 + s2 - 1;
-    const unsigned long long per_ct = (unsigned long long)nl << logn;
-    const unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t j = (uint32_t)(r >> logn);
-    const u64 m = mod[j], m0 = r0[j], m1 = r1[j];
-    for (unsigned long long ct = blockIdx.y; ct < n_ct; ct += gridDim.y) {
-        const u64 *a = A + ct * s1 * per_ct + r, *b = Bm + ct * s2 * per_ct + r;
-        u64 *d = D + ct * sd * per_ct + r;
-        behz_tensor_elem(a, b, d, per_ct, s1, s2, m, m0, m1);
-    }
-}
-
-// NTT over B_sk: one CTA per limb-polynomial, limb = blockIdx % nb
-template <int LOGN, int LOGE>
-__global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_nttw_fwd(const u64 *in, u64 *out, WideRing R)
-{
-    using S = NttShape<LOGN, LOGE>;
-    extern __shared__ u64 smem[];
-    const size_t p = blockIdx.x;
-    const int j = (int)(p % R.nb), tau = threadIdx.x;
-    const u64 *gin = in + p * S::N;
-    u64 *gout = out + p * S::N;
-    const W2 *tw = R.tw + (size_t)j * S::N;
-    const LimbWide lp = R.limb[j];
-    nttw_fwd_pass<LOGN, LOGE, 0>(tau, gin, gout, smem, tw, lp);
-    __syncthreads();
-    nttw_fwd_pass<LOGN, LOGE, 1>(tau, gin, gout, smem, tw, lp);
-    __syncthreads();
-    nttw_fwd_pass<LOGN, LOGE, 2>(tau, gin, gout, smem, tw, lp);
-    if constexpr (S::NPASS == 4) {
-        __syncthreads();
-        nttw_fwd_pass<LOGN, LOGE, 3>(tau, gin, gout, smem, tw, lp);
-    }
-    static_assert(S::NPASS == 3 || S::NPASS == 4, "3 or 4 passes");
-}
-template <int LOGN, int LOGE>
-__global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_nttw_inv(const u64 *in, u64 *out, WideRing R)
-{
-    using S = NttShape<LOGN, LOGE>;
-    static_assert(S::NPASS == 3 || S::NPASS == 4, "3 or 4 passes");
-    extern __shared__ u64 smem[];
-    const size_t p = blockIdx.x;
-    const int j = (int)(p % R.nb), tau = threadIdx.x;
-    const u64 *gin = in + p * S::N;
-    u64 *gout = out + p * S::N;
-    const W2 *itw = R.itw + (size_t)j * S::N;
-    const LimbWide lp = R.limb[j];
-    if constexpr (S::NPASS == 4) {
-        nttw_inv_pass<LOGN, LOGE, 3>(tau, gin, gout, smem, itw, lp);
-        __syncthreads();
-    }
-    nttw_inv_pass<LOGN, LOGE, 2>(tau, gin, gout, smem, itw, lp);
-    __syncthreads();
-    nttw_inv_pass<LOGN, LOGE, 1>(tau, gin, gout, smem, itw, lp);
-    __syncthreads();
-    nttw_inv_pass<LOGN, LOGE, 0>(tau, gin, gout, smem, itw, lp);
-}
 #endif  // __CUDACC__
 
 }  // namespace fhe

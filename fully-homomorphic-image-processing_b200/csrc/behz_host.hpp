@@ -11,18 +11,27 @@
 
 namespace fhe {
 
-// SEAL 2.3.1 internal_mods: the largest primes below 2^61 that are 1 mod 2^18, descending
-// (m_sk, gamma -- decryption only, unused here --, then aux_small_mods).
-static const u64 kMsk = 0x1fffffffffe00001ull;
-static const u64 kAuxSmallMods[10] = {0x1fffffffffb40001ull, 0x1fffffffff500001ull, 0x1fffffffff380001ull,
-                                      0x1fffffffff000001ull, 0x1ffffffffef00001ull, 0x1ffffffffee80001ull,
-                                      0x1ffffffffeb40001ull, 0x1ffffffffe780001ull, 0x1ffffffffe600001ull,
-                                      0x1ffffffffe4c0001ull};
+// The auxiliary primes: 2^55 - j 2^15 + 1 for j = 1, 2, 3 ... (1 mod 2^15, so every supported ring
+// degree has its 2n-th roots), prime, j not a multiple of 8 (SEAL's own coeff_modulus primes are 1 mod
+// 2^18: the defaults can never collide), and different from every prime of q.  The first is m_sk,
+// the next kb form B.  (SEAL 2.3 uses its 61-bit internal primes here; the result does not depend
+// on the base -- see behz.cuh.)
+inline std::vector<u64> h_aux_primes(size_t count, const std::vector<u64> &q)
+{
+    std::vector<u64> out;
+    for (u64 j = 1; out.size() < count && j < 2048; ++j) {
+        if (j % 8 == 0) continue;
+        const u64 p = (1ull << 55) - (j << 15) + 1;
+        bool clash = false;
+        for (u64 qi : q) clash |= qi == p;
+        if (!clash && h_is_prime(p)) out.push_back(p);
+    }
+    return out;
+}
 
 struct HostBehz {
     BehzDev dev{};
-    std::vector<LimbWide> limbs;            // B_sk
-    std::vector<std::vector<W2>> tw, itw;   // per B_sk prime, [n] per-pass layout, Shoup pairs scaled by 2^64
+    std::vector<HostLimb> limbs;  // B_sk, m_sk last: the same tables and constants as a limb of q
 };
 
 inline W2 h_shoup64(u64 w, u64 q) { return W2{w, (u64)((((u128)w) << 64) / q)}; }
@@ -46,17 +55,17 @@ inline bool build_behz(const HostRing &R, HostBehz &H, std::string &err)
     }
     const uint32_t tbits = 64 - __builtin_clzll(R.t);
     uint32_t kb = k;
-    if (32 + tbits + total_bits >= 61 * k + 61) ++kb;
+    // B m_sk must exceed 2 |W|, |W| < t n 32 q (behz.cuh); SEAL's rule 32 + bits(t) + bits(q) < bits(B_sk) is
+    // kept (it is the stricter one) with this base's 55-bit primes
+    if (32 + tbits + total_bits >= 55 * k + 55) ++kb;
     if (kb + 1 > (uint32_t)BEHZ_MAXB) { err = "auxiliary base too large"; return false; }
     const uint32_t nb = kb + 1;
+    const std::vector<u64> aux = h_aux_primes(nb, q);
+    if (aux.size() < nb) { err = "could not find the auxiliary primes"; return false; }
+    const u64 kMsk = aux[0];
     std::vector<u64> B(kb), bsk(nb);
-    for (uint32_t i = 0; i < kb; ++i) B[i] = bsk[i] = kAuxSmallMods[i];
+    for (uint32_t i = 0; i < kb; ++i) B[i] = bsk[i] = aux[1 + i];
     bsk[kb] = kMsk;
-    for (u64 p : bsk) {
-        if ((p - 1) % (2ull * n)) { err = "auxiliary prime is not 1 mod 2n"; return false; }
-        for (u64 qi : q)
-            if (qi == p) { err = "coeff_modulus collides with the auxiliary base"; return false; }
-    }
     BehzDev &D = H.dev;
     D = BehzDev{};
     D.n = n; D.logn = R.logn; D.k = k; D.kb = kb; D.nb = nb;
@@ -79,15 +88,13 @@ inline bool build_behz(const HostRing &R, HostBehz &H, std::string &err)
         for (int it = 0; it < 6; ++it) x = (x * (2 - qm * x)) & (MT - 1);
         D.neg_inv_q_mod_mt = (u32)(0 - x);
     }
-    H.limbs.assign(nb, LimbWide{});
-    H.tw.assign(nb, {}); H.itw.assign(nb, {});
+    H.limbs.assign(nb, HostLimb{});
     for (uint32_t j = 0; j < nb; ++j) {
         const u64 p = bsk[j];
         D.b[j] = p;
         const u128 ratio = (~(u128)0) / p;
         D.br0[j] = (u64)ratio; D.br1[j] = (u64)(ratio >> 64);
-        if (p >= (1ull << 61) || (1ull << 61) - p >= (1ull << 26)) { err = "auxiliary prime is not 2^61 - delta with delta < 2^26"; return false; }
-        D.bd8[j] = (u32)(8 * ((1ull << 61) - p));
+        D.bdelta[j] = (u32)((1ull << 55) - p);
         const u64 inv_mt = h_invmod(MT % p, p);
         const u64 q_mod = h_prod_except(q, none, p), q_inv = h_invmod(q_mod, p);
         const u64 dpos = h_mulmod(q_mod, inv_mt, p);
@@ -99,31 +106,7 @@ inline bool build_behz(const HostRing &R, HostBehz &H, std::string &err)
             const u64 f = h_mulmod(qhat, q_inv, p);
             D.F[j][i] = f ? p - f : 0;
         }
-        // NTT tables of this prime
-        LimbWide &L = H.limbs[j];
-        L.q = p; L.q2 = 2 * p; L.r0 = D.br0[j]; L.r1 = D.br1[j];
-        const u64 psi = h_min_primitive_root(p, n);
-        if (!psi) { err = "no primitive 2n-th root for an auxiliary prime"; return false; }
-        std::vector<u64> pw(n);
-        pw[0] = 1;
-        for (uint32_t i = 1; i < n; ++i) pw[i] = h_mulmod(pw[i - 1], psi, p);
-        std::vector<W2> seal_tw(n), seal_itw(n);
-        for (uint32_t idx = 0; idx < n; ++idx) {
-            const u64 w = pw[h_bitrev(idx, R.logn)];
-            seal_tw[idx] = h_shoup64(w, p);
-            seal_itw[idx] = h_shoup64(h_invmod(w, p), p);
-        }
-        H.tw[j].assign(n, W2{0, 0}); H.itw[j].assign(n, W2{0, 0});
-        switch (R.logn) {
-        case 10: ntt_permute_table<10, 4>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<10, 4>(seal_itw.data(), H.itw[j].data()); break;
-        case 11: ntt_permute_table<11, 4>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<11, 4>(seal_itw.data(), H.itw[j].data()); break;
-        case 12: ntt_permute_table<12, 4>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<12, 4>(seal_itw.data(), H.itw[j].data()); break;
-        case 13: ntt_permute_table<13, FHE_LOGE13>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<13, FHE_LOGE13>(seal_itw.data(), H.itw[j].data()); break;
-        case 14: ntt_permute_table<14, FHE_LOGE14>(seal_tw.data(), H.tw[j].data()); ntt_permute_table<14, FHE_LOGE14>(seal_itw.data(), H.itw[j].data()); break;
-        }
-        const u64 ninv = h_invmod(n % p, p);
-        L.ninv = h_shoup64(ninv, p);
-        L.ninv_w1 = h_shoup64(h_mulmod(ninv, seal_itw[1].w, p), p);
+        if (!h_build_limb(H.limbs[j], p, n, R.logn, err)) return false;
     }
     const u64 invB = h_invmod(h_prod_except(B, none, kMsk), kMsk);
     D.H = kMsk - invB;

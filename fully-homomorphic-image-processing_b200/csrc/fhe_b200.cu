@@ -1219,4 +1219,5 @@ int fhe_checksum(fhe_ctx *c, const uint64_t *d, uint64_t count, uint64_t *out)
 }  // extern "C"
 
 #include "behz_api.inc"
+#include "resize_api.inc"
 #include "jpeg_api.inc"

@@ -98,6 +98,41 @@ inline u64 h_min_primitive_root(u64 q, uint32_t n)
     return best;
 }
 
+// NTT tables and arithmetic constants of one prime (q < 2^55 for the lazy arithmetic, 1 mod 2n)
+inline bool h_build_limb(HostLimb &L, u64 qj, uint32_t n, uint32_t logn, std::string &err)
+{
+    L.q = qj;
+    u128 ratio = (~(u128)0) / qj;  // floor(2^128/q): q odd, never divides 2^128
+    L.ratio0 = (u64)ratio; L.ratio1 = (u64)(ratio >> 64);
+    L.psi = h_min_primitive_root(qj, n);
+    if (!L.psi) { err = "no primitive 2n-th root found"; return false; }
+    std::vector<u64> pw(n);
+    pw[0] = 1;
+    for (uint32_t i = 1; i < n; ++i) pw[i] = h_mulmod(pw[i - 1], L.psi, qj);
+    std::vector<W2> seal_tw(n), seal_itw(n);
+    for (uint32_t idx = 0; idx < n; ++idx) {
+        u64 w = pw[h_bitrev(idx, logn)];
+        seal_tw[idx] = h_shoup(w, qj);
+        seal_itw[idx] = h_shoup(h_invmod(w, qj), qj);
+    }
+    L.tw.assign(n, W2{0, 0}); L.itw.assign(n, W2{0, 0});
+    switch (logn) {
+    case 10: ntt_permute_table<10, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<10, 4>(seal_itw.data(), L.itw.data()); break;
+    case 11: ntt_permute_table<11, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<11, 4>(seal_itw.data(), L.itw.data()); break;
+    case 12: ntt_permute_table<12, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<12, 4>(seal_itw.data(), L.itw.data()); break;
+    case 13: ntt_permute_table<13, FHE_LOGE13>(seal_tw.data(), L.tw.data()); ntt_permute_table<13, FHE_LOGE13>(seal_itw.data(), L.itw.data()); break;
+    case 14: ntt_permute_table<14, FHE_LOGE14>(seal_tw.data(), L.tw.data()); ntt_permute_table<14, FHE_LOGE14>(seal_itw.data(), L.itw.data()); break;
+    default: err = "unsupported ring degree"; return false;
+    }
+    u64 ninv = h_invmod(n % qj, qj);
+    L.itw1 = seal_itw[1].w;
+    L.dev.a = h_limb_arith(qj);
+    L.dev.ninv = h_shoup(ninv, qj);
+    L.dev.ninv_w1 = h_shoup(h_mulmod(ninv, L.itw1, qj), qj);
+    L.dev.iw1 = seal_itw[1];
+    return true;
+}
+
 inline bool build_ring(HostRing &R, uint32_t n, uint32_t k, const uint64_t *q, u64 t, std::string &err)
 {
     if (n < 1024 || n > 16384 || (n & (n - 1))) { err = "poly_modulus degree must be a power of two in [1024, 16384]"; return false; }
@@ -120,34 +155,7 @@ inline bool build_ring(HostRing &R, uint32_t n, uint32_t k, const uint64_t *q, u
             if (q[i] == qj) { err = "coeff_modulus primes must be distinct"; return false; }
         int bits = 64 - __builtin_clzll(qj);
         if (bits > R.max_qbits) R.max_qbits = bits;
-        L.q = qj;
-        u128 ratio = (~(u128)0) / qj;  // floor(2^128/q): q odd, never divides 2^128
-        L.ratio0 = (u64)ratio; L.ratio1 = (u64)(ratio >> 64);
-        L.psi = h_min_primitive_root(qj, n);
-        if (!L.psi) { err = "no primitive 2n-th root found"; return false; }
-        std::vector<u64> pw(n);
-        pw[0] = 1;
-        for (uint32_t i = 1; i < n; ++i) pw[i] = h_mulmod(pw[i - 1], L.psi, qj);
-        std::vector<W2> seal_tw(n), seal_itw(n);
-        for (uint32_t idx = 0; idx < n; ++idx) {
-            u64 w = pw[h_bitrev(idx, R.logn)];
-            seal_tw[idx] = h_shoup(w, qj);
-            seal_itw[idx] = h_shoup(h_invmod(w, qj), qj);
-        }
-        L.tw.assign(n, W2{0, 0}); L.itw.assign(n, W2{0, 0});
-        switch (R.logn) {
-        case 10: ntt_permute_table<10, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<10, 4>(seal_itw.data(), L.itw.data()); break;
-        case 11: ntt_permute_table<11, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<11, 4>(seal_itw.data(), L.itw.data()); break;
-        case 12: ntt_permute_table<12, 4>(seal_tw.data(), L.tw.data()); ntt_permute_table<12, 4>(seal_itw.data(), L.itw.data()); break;
-        case 13: ntt_permute_table<13, FHE_LOGE13>(seal_tw.data(), L.tw.data()); ntt_permute_table<13, FHE_LOGE13>(seal_itw.data(), L.itw.data()); break;
-        case 14: ntt_permute_table<14, FHE_LOGE14>(seal_tw.data(), L.tw.data()); ntt_permute_table<14, FHE_LOGE14>(seal_itw.data(), L.itw.data()); break;
-        }
-        u64 ninv = h_invmod(n % qj, qj);
-        L.itw1 = seal_itw[1].w;
-        L.dev.a = h_limb_arith(qj);
-        L.dev.ninv = h_shoup(ninv, qj);
-        L.dev.ninv_w1 = h_shoup(h_mulmod(ninv, L.itw1, qj), qj);
-        L.dev.iw1 = seal_itw[1];
+        if (!h_build_limb(L, qj, n, R.logn, err)) return false;
     }
     // q = prod q_j (multi-word), Delta = floor(q/t), q mod t
     std::vector<u64> big(1, 1);

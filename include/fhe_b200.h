@@ -173,7 +173,8 @@ int fhe_encrypt_transparent(fhe_ctx *ctx, const uint64_t *plain, uint32_t count,
 /* ---- Evaluator: ciphertext x ciphertext ----------------------------------------------------
  * Evaluator::multiply(a, b) (fhe_resize.h:175-179,197-198; fhe_decode.h:71-97,235,239): BFV tensor
  * product with the BEHZ full-RNS scaling round(t/q .) (SEAL 2.3 [SEAL-recall], SURVEY.md Appendix
- * A.6; auxiliary base and m_sk = SEAL's 61-bit internal primes).  n_ct independent pairs:
+ * A.6).  The auxiliary base is this library's own (55-bit primes, csrc/behz.cuh): the result of the
+ * procedure does not depend on it, and is compared bit for bit with the oracle's SEAL base.  n_ct independent pairs:
  * a [n_ct][size_a][k][n], b [n_ct][size_b][k][n] -> dest [n_ct][size_a + size_b - 1][k][n].
  * The reference's in-place form `evaluator.multiply(a, b)` is dest -> a afterwards (sizes differ,
  * so dest must be a separate buffer and must not overlap the operands).  Sizes up to 32
@@ -184,6 +185,48 @@ int fhe_multiply(fhe_ctx *ctx, const uint64_t *a, uint32_t size_a, const uint64_
 /* Evaluator::square(a) (fhe_resize.h:174, fhe_decode.h:67...): same result as multiply(a, a), the
  * operand is extended and transformed once. */
 int fhe_square(fhe_ctx *ctx, const uint64_t *a, uint32_t size_a, uint64_t *dest, uint64_t n_ct);
+
+/* Operand forms.  Evaluator::multiply transforms each operand (BEHZ extension q -> B_sk, forward NTT in
+ * every modulus of q and B_sk) before the tensor step.  The reference's graphs multiply by the same
+ * ciphertext over and over -- t, t2 and "t3" of Cubic are shared by the 4 rows x 3 channels of an output
+ * pixel (fhe_resize.h:174-179, 296-303), shifted_x by four products of each Taylor series
+ * (fhe_decode.h:79-97) -- so the transformed operand is exposed as a handle: fhe_form_create does the
+ * operand half of fhe_multiply once for n_ct ciphertexts [n_ct][size][k][n]; fhe_multiply_form does the
+ * rest for n_ct products, product i taking ciphertext i / a_div of `a` and i / b_div of `b` (a_div = 1:
+ * one operand per product; 3: three consecutive products share one).  dest
+ * [n_ct][a.size + b.size - 1][k][n] is bit-identical to fhe_multiply on the same ciphertexts (same
+ * arithmetic, transformed once).  a == b (same handle, same divisor) is Evaluator::square. */
+typedef struct fhe_form fhe_form;
+int fhe_form_create(fhe_ctx *ctx, const uint64_t *d_ct, uint32_t size, uint64_t n_ct, fhe_form **out);
+void fhe_form_destroy(fhe_form *form);
+int fhe_multiply_form(fhe_ctx *ctx, const fhe_form *a, uint32_t a_div, const fhe_form *b, uint32_t b_div,
+                      uint64_t *dest, uint64_t n_ct);
+
+/* ---- resize graphs: Cubic and Linear (fhe_resize.h:143-189, :191-204) as fused device graphs --------
+ * The same ciphertexts as the reference's op-by-op evaluation (every step is exact arithmetic with
+ * canonical results and BEHZ multiply is a deterministic function of its operands), computed for n_ct
+ * independent calls at once in 6 (Cubic) / 5 (Linear) kernel launches:
+ *   gather + linear combinations + BEHZ extension -> forward transforms -> tensor products with the
+ *   CACHED forms of the fraction powers fused with the inverse transforms -> BEHZ scaling + sum
+ *   (+ x encode(0.5) + d).
+ * taps: HOST array [n_ct][4] (Cubic: A B C D) or [n_ct][2] (Linear: A B) of DEVICE pointers to
+ * ciphertexts of size_in polynomials ([size_in][k][n]); the 4 x 4 neighbourhood of an output pixel
+ * (fhe_resize.h:269-290) is read in place through the table, never copied.
+ * Cubic: t (size 2), t2 = square(t) and t3 = multiply(t, t) (sic, fhe_resize.h:174-175; equal sizes)
+ * as forms; call i uses ciphertext i / t_div of each.  dest [n_ct][size_in + t2.size - 1][k][n].
+ * Linear: one_minus_t = negate(t) + encode(1.0) and t as forms; dest [n_ct][size_in + t.size - 1][k][n].
+ * fhe_resize_plan_create: plains = [5][n] coefficients of encode(3), encode(2), encode(5), encode(4),
+ * encode(0.5) from the caller's FractionalEncoder (fhe_resize.h:151-183); FHE_ERR_UNSUPPORTED when
+ * they are not short +-1 polynomials (binary FractionalEncoder encodings always are) -- the caller
+ * then composes the graph from the Evaluator entry points. */
+typedef struct fhe_resize_plan fhe_resize_plan;
+int fhe_resize_plan_create(fhe_ctx *ctx, const uint64_t *plains, fhe_resize_plan **out);
+void fhe_resize_plan_destroy(fhe_resize_plan *plan);
+int fhe_cubic(fhe_ctx *ctx, const fhe_resize_plan *plan, const uint64_t *const *taps, uint32_t size_in,
+              const fhe_form *t, const fhe_form *t2, const fhe_form *t3, uint32_t t_div, uint64_t *dest,
+              uint64_t n_ct);
+int fhe_linear(fhe_ctx *ctx, const uint64_t *const *taps, uint32_t size_in, const fhe_form *one_minus_t,
+               const fhe_form *t, uint32_t t_div, uint64_t *dest, uint64_t n_ct);
 
 /* Evaluator::relinearize(ct, evk) (no call site in homo/; keys at tests/parameters.cpp:89-90,
  * decomposition_bit_count = DBC fhe_image.h:28).

@@ -208,13 +208,16 @@ class Behz:
     an exact integer division -- no Barrett, no NTT, no 128-bit accumulators, so nothing is shared
     with oracle/fhe_oracle_behz.c or the CUDA kernels beyond the specification itself."""
 
-    def __init__(self, m: Model):
+    def __init__(self, m: Model, bsk: list[int] | None = None):
+        """bsk: another auxiliary base B + [m_sk] (the CUDA library uses 55-bit primes, csrc/behz.cuh);
+        default: SEAL's.  The products do not depend on it (tests/test_oracle_behz.py)."""
         self.m = m
         k = len(m.qs)
         bits = sum(q.bit_length() for q in m.qs)
         kb = k + (1 if 32 + m.t.bit_length() + bits >= 61 * k + 61 else 0)
-        self.B = AUX_SMALL_MODS[:kb]
-        self.bsk = self.B + [M_SK]
+        self.B = list(bsk[:-1]) if bsk else AUX_SMALL_MODS[:kb]
+        self.msk = bsk[-1] if bsk else M_SK
+        self.bsk = self.B + [self.msk]
         self.Bprod = prod(self.B)
 
     def _conv_sum(self, res, mods, total):
@@ -248,9 +251,9 @@ class Behz:
             s = self._conv_sum([t * xq[i][c] % qi for i, qi in enumerate(m.qs)], m.qs, q)
             f = [(t * xb[j][c] - s) * pow(q, -1, p) % p for j, p in enumerate(self.bsk)]
             s2 = self._conv_sum(f[:-1], self.B, self.Bprod)
-            alpha = (s2 - f[-1]) * pow(self.Bprod, -1, M_SK) % M_SK
-            if alpha > M_SK // 2:
-                alpha -= M_SK
+            alpha = (s2 - f[-1]) * pow(self.Bprod, -1, self.msk) % self.msk
+            if alpha > self.msk // 2:
+                alpha -= self.msk
             out.append((s2 - alpha * self.Bprod) % q)   # CRT of the per-limb results
         return out
 

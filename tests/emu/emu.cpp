@@ -56,10 +56,9 @@ static void emu_inv(const HostLimb &L, const u64 *in, u64 *out, bool scale)
     pass(ic<0>{});
 }
 
-static int fwd_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, int mode)
+static int fwd_limb(const HostLimb &L, uint32_t logn, const u64 *in, u64 *out, int mode)
 {
-    const HostLimb &L = R.limbs[j];
-    switch (R.logn) {
+    switch (logn) {
     case 10: emu_fwd<10, 4>(L, in, out, mode); return 0;
     case 11: emu_fwd<11, 4>(L, in, out, mode); return 0;
     case 12: emu_fwd<12, 4>(L, in, out, mode); return 0;
@@ -68,10 +67,10 @@ static int fwd_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, int m
     default: return -1;
     }
 }
-static int inv_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, bool scale)
+static int fwd_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, int mode) { return fwd_limb(R.limbs[j], R.logn, in, out, mode); }
+static int inv_limb(const HostLimb &L, uint32_t logn, const u64 *in, u64 *out, bool scale)
 {
-    const HostLimb &L = R.limbs[j];
-    switch (R.logn) {
+    switch (logn) {
     case 10: emu_inv<10, 4>(L, in, out, scale); return 0;
     case 11: emu_inv<11, 4>(L, in, out, scale); return 0;
     case 12: emu_inv<12, 4>(L, in, out, scale); return 0;
@@ -81,50 +80,10 @@ static int inv_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, bool 
     }
 }
 
-template <int LOGN, int LOGE>
-static void emu_fwd_w(const HostBehz &H, int j, const u64 *in, u64 *out)
-{
-    using S = NttShape<LOGN, LOGE>;
-    std::vector<u64> smem(S::SMEM_WORDS), tmp(in, in + S::N);
-    for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 0>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
-    for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 1>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
-    for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 2>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
-    if constexpr (S::NPASS == 4)
-        for (int tau = 0; tau < S::T; ++tau) nttw_fwd_pass<LOGN, LOGE, 3>(tau, tmp.data(), out, smem.data(), H.tw[j].data(), H.limbs[j]);
-}
-template <int LOGN, int LOGE>
-static void emu_inv_w(const HostBehz &H, int j, const u64 *in, u64 *out)
-{
-    using S = NttShape<LOGN, LOGE>;
-    std::vector<u64> smem(S::SMEM_WORDS), tmp(in, in + S::N);
-    if constexpr (S::NPASS == 4)
-        for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 3>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
-    for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 2>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
-    for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 1>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
-    for (int tau = 0; tau < S::T; ++tau) nttw_inv_pass<LOGN, LOGE, 0>(tau, tmp.data(), out, smem.data(), H.itw[j].data(), H.limbs[j]);
-}
-static int fwd_w_dispatch(const HostBehz &H, int j, const u64 *in, u64 *out)
-{
-    switch (H.dev.logn) {
-    case 10: emu_fwd_w<10, 4>(H, j, in, out); return 0;
-    case 11: emu_fwd_w<11, 4>(H, j, in, out); return 0;
-    case 12: emu_fwd_w<12, 4>(H, j, in, out); return 0;
-    case 13: emu_fwd_w<13, FHE_LOGE13>(H, j, in, out); return 0;
-    case 14: emu_fwd_w<14, FHE_LOGE14>(H, j, in, out); return 0;
-    default: return -1;
-    }
-}
-static int inv_w_dispatch(const HostBehz &H, int j, const u64 *in, u64 *out)
-{
-    switch (H.dev.logn) {
-    case 10: emu_inv_w<10, 4>(H, j, in, out); return 0;
-    case 11: emu_inv_w<11, 4>(H, j, in, out); return 0;
-    case 12: emu_inv_w<12, 4>(H, j, in, out); return 0;
-    case 13: emu_inv_w<13, FHE_LOGE13>(H, j, in, out); return 0;
-    case 14: emu_inv_w<14, FHE_LOGE14>(H, j, in, out); return 0;
-    default: return -1;
-    }
-}
+static int inv_dispatch(const HostRing &R, int j, const u64 *in, u64 *out, bool scale) { return inv_limb(R.limbs[j], R.logn, in, out, scale); }
+// the B_sk limbs run the same transforms as the q limbs (csrc/behz.cuh: 55-bit auxiliary primes)
+static int fwd_w_dispatch(const HostBehz &H, int j, const u64 *in, u64 *out) { return fwd_limb(H.limbs[j], H.dev.logn, in, out, NTT_OUT_CANON); }
+static int inv_w_dispatch(const HostBehz &H, int j, const u64 *in, u64 *out) { return inv_limb(H.limbs[j], H.dev.logn, in, out, true); }
 
 extern "C" {
 
@@ -141,6 +100,7 @@ void *emu_behz_create(void *ring, char *err, int errlen)
 }
 void emu_behz_destroy(void *h) { delete (HostBehz *)h; }
 uint32_t emu_behz_nb(void *h) { return ((HostBehz *)h)->dev.nb; }
+uint64_t emu_behz_bsk(void *h, int j) { return ((HostBehz *)h)->dev.b[j]; }
 int emu_nttw_forward(void *h, int j, const uint64_t *in, uint64_t *out) { return fwd_w_dispatch(*(HostBehz *)h, j, (const u64 *)in, (u64 *)out); }
 int emu_nttw_inverse(void *h, int j, const uint64_t *in, uint64_t *out) { return inv_w_dispatch(*(HostBehz *)h, j, (const u64 *)in, (u64 *)out); }
 // x [k][n] -> out [nb][n]
@@ -186,10 +146,10 @@ int emu_multiply(void *ring, void *h, const uint64_t *a1, uint32_t s1, const uin
     return 0;
 }
 
-// z = z1 2^64 + z0 mod p (p = 2^61 - delta), the special-prime reduction of csrc/behz.cuh
-uint64_t emu_fold61(uint64_t z0, uint64_t z1, uint64_t p)
+// z = z1 2^64 + z0 (< 2^119) mod p (p = 2^55 - delta), the special-prime reduction of csrc/behz.cuh
+uint64_t emu_fold_aux(uint64_t z0, uint64_t z1, uint64_t p)
 {
-    return fold61(((u128d)z1 << 64) | z0, p, (u32)(8 * ((1ull << 61) - p)));
+    return fold_aux(((u128d)z1 << 64) | z0, p, (u32)((1ull << 55) - p));
 }
 
 void *emu_ring_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, char *err, int errlen)

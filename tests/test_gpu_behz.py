@@ -181,3 +181,42 @@ def test_multiply_then_relinearize_decrypts(gpu, oracle_mod):
     for d in (da, db, d3, d2):
         ctx.free(d)
     ctx.close()
+
+
+@pytest.mark.parametrize("n,sa,sb,groups,div", [(4096, 2, 3, 4, 3), (8192, 4, 3, 2, 3), (8192, 2, 2, 5, 1), (2048, 2, 2, 3, 2)])
+def test_multiply_form_shares_operands_and_matches_multiply(gpu, oracle_mod, n, sa, sb, groups, div):
+    """fhe_form_create / fhe_multiply_form: the transformed operand is built once and serves `div`
+    consecutive products (the three colour channels share the fraction powers in Cubic); results are
+    the oracle's multiply bit for bit, and a form times itself is square."""
+    q = oracle_mod.default_coeff_modulus(n)
+    ctx, o = gpu.Context(n, q), oracle_mod.Oracle(n, q)
+    n_ct = groups * div
+    a = o.fill_uniform(10, n_ct, sa, 0xF0A1)
+    b = o.fill_uniform(50, groups, sb, 0xF0B2)
+    da, db = ctx.to_device(a), ctx.to_device(b)
+    fa, fb = ctx.form(da, sa, n_ct), ctx.form(db, sb, groups)
+    sd = sa + sb - 1
+    dd = ctx.alloc(n_ct * ctx.ct_bytes(sd))
+    ctx.multiply_form(fa, 1, fb, div, dd, n_ct)
+    got = fetch(ctx, dd, n_ct * ctx.ct_words(sd))
+    wa, wb, wd = ctx.ct_words(sa), ctx.ct_words(sb), ctx.ct_words(sd)
+    for i in range(n_ct):
+        g = i // div
+        ref = o.multiply(a[i * wa:(i + 1) * wa], sa, b[g * wb:(g + 1) * wb], sb)
+        assert (got[i * wd:(i + 1) * wd] == ref).all(), (n, i)
+    # operand order does not matter; a form times itself is Evaluator::square
+    ctx.multiply_form(fb, div, fa, 1, dd, n_ct)
+    assert (fetch(ctx, dd, n_ct * ctx.ct_words(sd)) == got).all()
+    d2 = ctx.alloc(groups * ctx.ct_bytes(2 * sb - 1))
+    ctx.multiply_form(fb, 1, fb, 1, d2, groups)
+    sq = fetch(ctx, d2, groups * ctx.ct_words(2 * sb - 1))
+    w2 = ctx.ct_words(2 * sb - 1)
+    for g in range(groups):
+        assert (sq[g * w2:(g + 1) * w2] == o.square(b[g * wb:(g + 1) * wb], sb)).all()
+    if div > 1:
+        with pytest.raises(gpu.FheError):
+            ctx.multiply_form(fa, 1, fb, 1, dd, n_ct)      # fb has too few ciphertexts for divisor 1
+    fa.close(); fb.close()
+    for d in (da, db, dd, d2):
+        ctx.free(d)
+    ctx.close()
