@@ -115,6 +115,8 @@ def lib():
         "fhe_form_create": (i32, [vp, vp, u32, u64, C.POINTER(vp)]),
         "fhe_form_destroy": (None, [vp]),
         "fhe_multiply_form": (i32, [vp, vp, u32, vp, u32, vp, u64]),
+        "fhe_profile_begin": (i32, [vp]),
+        "fhe_profile_end": (i32, [vp, C.c_char_p, C.c_size_t, C.POINTER(C.c_float), u64p, u32, C.POINTER(u32)]),
         "fhe_resize_plan_create": (i32, [vp, u64p, C.POINTER(vp)]),
         "fhe_resize_plan_destroy": (None, [vp]),
         "fhe_cubic": (i32, [vp, vp, C.POINTER(vp), u32, vp, vp, vp, u32, vp, u64]),
@@ -139,13 +141,21 @@ EXPORTED_SYMBOLS = (
     "fhe_ntt_forward", "fhe_ntt_inverse", "fhe_dct_plan_create", "fhe_dct_plan_destroy",
     "fhe_dct8x8_quantize", "fhe_dct8x8_quantize_host", "fhe_fill_uniform", "fhe_checksum",
     "fhe_launch_count", "fhe_set_dct_chunk_blocks", "fhe_set_stage_timing", "fhe_get_stage_times",
-    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_encrypt_transparent", "fhe_ntt_loge", "fhe_multiply", "fhe_square", "fhe_form_create", "fhe_form_destroy", "fhe_multiply_form", "fhe_resize_plan_create", "fhe_resize_plan_destroy", "fhe_cubic", "fhe_linear", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
+    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_encrypt_transparent", "fhe_ntt_loge", "fhe_multiply", "fhe_square", "fhe_form_create", "fhe_form_destroy", "fhe_multiply_form", "fhe_profile_begin", "fhe_profile_end", "fhe_resize_plan_create", "fhe_resize_plan_destroy", "fhe_cubic", "fhe_linear", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
 )
 
 
 def _check(rc):
     if rc != 0:
         raise FheError(rc, lib().fhe_last_error().decode())
+
+
+def profile_end_handle(h) -> dict:
+    names = C.create_string_buffer(4096)
+    ms, counts, n = (C.c_float * 64)(), (C.c_uint64 * 64)(), C.c_uint32(0)
+    _check(lib().fhe_profile_end(h, names, 4096, ms, counts, 64, C.byref(n)))
+    keys = names.value.decode().split("\n")
+    return {keys[i]: (float(ms[i]), int(counts[i])) for i in range(n.value)}
 
 
 def coeff_modulus_128(n: int) -> list[int]:
@@ -212,6 +222,12 @@ class Context:
         return d
 
     def sync(self): _check(lib().fhe_ctx_sync(self.h))
+
+    def profile_begin(self): _check(lib().fhe_profile_begin(self.h))
+
+    def profile_end(self) -> dict:
+        """{kernel: (summed device ms, launches)} since profile_begin (include/fhe_b200.h)"""
+        return profile_end_handle(self.h)
     def launch_count(self) -> int: return int(lib().fhe_launch_count(self.h))
     def set_dct_chunk_blocks(self, blocks: int): _check(lib().fhe_set_dct_chunk_blocks(self.h, blocks))
     def set_stage_timing(self, on: bool): _check(lib().fhe_set_stage_timing(self.h, int(on)))

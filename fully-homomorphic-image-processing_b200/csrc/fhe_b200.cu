@@ -409,6 +409,9 @@ struct fhe_ctx {
     u64 *h_ring = nullptr;
     cudaEvent_t ev_ring[kRing]{};
     uint64_t ring_next = 0;
+    // per-kernel device time (fhe_profile_begin / fhe_profile_end): an event after every launch
+    bool prof_on = false;
+    std::vector<std::pair<const char *, cudaEvent_t>> prof_marks;
     // Evaluator::multiply / square / relinearize state, built on first use (behz_api.inc)
     struct BehzState *behz = nullptr;
 };
@@ -430,6 +433,19 @@ struct fhe_dct_plan {
     W2 *d_s = nullptr;  // [64][k][n]
     bool has_quant = false;
 };
+
+// every kernel launch of the library passes here
+static inline void launched(fhe_ctx *c, const char *kernel)
+{
+    c->launches++;
+    if (c->prof_on) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) == cudaSuccess) {
+            cudaEventRecord(e, c->stream);
+            c->prof_marks.emplace_back(kernel, e);
+        }
+    }
+}
 
 static void clear_stage_events(fhe_ctx *c)
 {
@@ -469,7 +485,7 @@ static int launch_fwd_mode(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, 
     const size_t smem = S::SMEM_WORDS * sizeof(u64);
     if (int rc = set_smem(k_ntt_fwd<LOGN, LOGE, OUT>, smem)) return rc;
     k_ntt_fwd<LOGN, LOGE, OUT><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
-    c->launches++;
+    launched(c, "k_ntt_fwd");
     CU_TRY(cudaGetLastError());
     return FHE_OK;
 }
@@ -486,7 +502,7 @@ static int launch_inv(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, cudaS
     const size_t smem = S::SMEM_WORDS * sizeof(u64);
     if (int rc = set_smem(k_ntt_inv<LOGN, LOGE, SCALE>, smem)) return rc;
     k_ntt_inv<LOGN, LOGE, SCALE><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
-    c->launches++;
+    launched(c, "k_ntt_inv");
     CU_TRY(cudaGetLastError());
     return FHE_OK;
 }
@@ -497,7 +513,7 @@ static int launch_mulplain(fhe_ctx *c, const u64 *in, u64 *out, const W2 *tab, u
     const size_t smem = S::SMEM_WORDS * sizeof(u64);
     if (int rc = set_smem(k_mulplain<LOGN, LOGE>, smem)) return rc;
     k_mulplain<LOGN, LOGE><<<(unsigned)npoly, S::T, smem, st>>>(in, out, tab, c->dev);
-    c->launches++;
+    launched(c, "k_mulplain");
     CU_TRY(cudaGetLastError());
     return FHE_OK;
 }
@@ -633,6 +649,7 @@ void fhe_ctx_destroy(fhe_ctx *c)
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
     clear_stage_events(c);
+    for (auto &m : c->prof_marks) cudaEventDestroy(m.second);
     for (auto &kv : c->alloc_size) cudaFreeAsync(kv.first, c->stream);  // parked and still-live blocks alike
     cudaStreamSynchronize(c->stream);
     behz_state_destroy(c->behz);
@@ -682,6 +699,50 @@ int fhe_get_stage_times(fhe_ctx *c, float *ms)
             CU_TRY(cudaEventElapsedTime(&t, c->stage_ev[i + s], c->stage_ev[i + s + 1]));
             ms[s] += t;
         }
+    return FHE_OK;
+}
+
+int fhe_profile_begin(fhe_ctx *c)
+{
+    if (int rc = check_ctx(c)) return rc;
+    for (auto &m : c->prof_marks) cudaEventDestroy(m.second);
+    c->prof_marks.clear();
+    c->prof_on = true;
+    launched(c, "");  // the start mark (not a kernel)
+    c->launches--;
+    return FHE_OK;
+}
+int fhe_profile_end(fhe_ctx *c, char *names, size_t names_len, float *ms, uint64_t *counts, uint32_t max_kernels, uint32_t *n_out)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!names || !ms || !counts || !n_out) return fail(FHE_ERR_INVALID_ARGUMENT, "null output");
+    c->prof_on = false;
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    std::vector<std::string> order;
+    std::unordered_map<std::string, std::pair<float, uint64_t>> acc;
+    for (size_t i = 1; i < c->prof_marks.size(); ++i) {
+        float t = 0.f;
+        CU_TRY(cudaEventElapsedTime(&t, c->prof_marks[i - 1].second, c->prof_marks[i].second));
+        const std::string k = c->prof_marks[i].first;
+        if (!acc.count(k)) order.push_back(k);
+        acc[k].first += t;
+        acc[k].second += 1;
+    }
+    for (auto &m : c->prof_marks) cudaEventDestroy(m.second);
+    c->prof_marks.clear();
+    std::string joined;
+    uint32_t n = 0;
+    for (const std::string &k : order) {
+        if (n == max_kernels) break;
+        if (joined.size() + k.size() + 2 > names_len) break;
+        joined += k;
+        joined += '\n';
+        ms[n] = acc[k].first;
+        counts[n] = acc[k].second;
+        ++n;
+    }
+    std::memcpy(names, joined.c_str(), joined.size() + 1);
+    *n_out = n;
     return FHE_OK;
 }
 
@@ -823,7 +884,7 @@ static int elementwise(fhe_ctx *c, int op, u64 *a, const u64 *b, uint64_t n_ct, 
     if (op == 0) k_elementwise<0><<<g, 256, 0, c->stream>>>(a, b, total, c->dev);
     else if (op == 1) k_elementwise<1><<<g, 256, 0, c->stream>>>(a, b, total, c->dev);
     else k_elementwise<2><<<g, 256, 0, c->stream>>>(a, nullptr, total, c->dev);
-    c->launches++;
+    launched(c, "k_elementwise");
     CU_TRY(cudaGetLastError());
     return FHE_OK;
 }
@@ -870,11 +931,11 @@ static int build_plain_tables(fhe_ctx *c, const uint64_t *plain, uint32_t count,
     do {
         if (cudaMemcpyAsync(d_plain, plain, (size_t)count * n * sizeof(u64), cudaMemcpyHostToDevice, c->stream) != cudaSuccess) { rc = fail(FHE_ERR_CUDA, "plaintext upload failed"); break; }
         const int g = grid_for(total, 256, c->sm_count);
-        if (d_scaled) { k_plain_scale<<<g, 256, 0, c->stream>>>(d_plain, d_scaled, total, c->dev); c->launches++; }
+        if (d_scaled) { k_plain_scale<<<g, 256, 0, c->stream>>>(d_plain, d_scaled, total, c->dev); launched(c, "k_plain_scale"); }
         k_plain_lift<<<g, 256, 0, c->stream>>>(d_plain, d_lift, total, c->dev);
-        c->launches++;
+        launched(c, "k_plain_lift");
         if ((rc = ntt_forward(c, d_lift, d_lift, (uint64_t)count * k, NTT_OUT_CANON, c->stream))) break;
-        if (d_ntt) { k_make_shoup<<<g, 256, 0, c->stream>>>(d_lift, nullptr, d_ntt, total, 1, ntt_times_ninv, c->dev); c->launches++; }
+        if (d_ntt) { k_make_shoup<<<g, 256, 0, c->stream>>>(d_lift, nullptr, d_ntt, total, 1, ntt_times_ninv, c->dev); launched(c, "k_make_shoup"); }
         if (d_values_out && cudaMemcpyAsync(d_values_out, d_lift, total * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { rc = fail(FHE_ERR_CUDA, "table copy failed"); break; }
         if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = fail(FHE_ERR_CUDA, "plaintext table kernels failed"); break; }
     } while (0);
@@ -933,7 +994,7 @@ int fhe_encrypt_transparent(fhe_ctx *c, const uint64_t *plain, uint32_t count, u
     }
     const unsigned long long total = (unsigned long long)count * 2 * k * n;
     k_encrypt_transparent<<<grid_for(total, 256, c->sm_count), 256, 0, c->stream>>>(d_plain, (u64 *)d_dst, total, c->dev);
-    c->launches++;
+    launched(c, "k_encrypt_transparent");
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaFreeAsync(d_plain, c->stream));
     return FHE_OK;
@@ -1001,7 +1062,7 @@ int fhe_multiply_plain(fhe_ctx *c, uint64_t *a, uint64_t n_ct, uint32_t size, co
         const size_t smem = (size_t)c->host.n * sizeof(u64);
         if (int rc = set_smem(k_mulplain_sparse, smem)) return rc;
         k_mulplain_sparse<<<(unsigned)npoly, 256, smem, c->stream>>>((u64 *)a, T, c->dev);
-        c->launches++;
+        launched(c, "k_mulplain_sparse");
         CU_TRY(cudaGetLastError());
         return FHE_OK;
     }
@@ -1022,7 +1083,7 @@ static int plain_addsub(fhe_ctx *c, int sign, uint64_t *a, uint64_t n_ct, uint32
     const int g = grid_for(total, 256, c->sm_count);
     if (sign > 0) k_plain_addsub<1><<<g, 256, 0, c->stream>>>((u64 *)a, scaled, n_ct, size, c->dev);
     else k_plain_addsub<-1><<<g, 256, 0, c->stream>>>((u64 *)a, scaled, n_ct, size, c->dev);
-    c->launches++;
+    launched(c, "k_plain_addsub");
     CU_TRY(cudaGetLastError());
     return FHE_OK;
 }
@@ -1064,7 +1125,7 @@ int fhe_dct_plan_create(fhe_ctx *c, const uint64_t *dct_consts, const uint64_t *
             for (int i = 0; i < 64; ++i) cudaMemcpyAsync(d_q + (size_t)i * per, d_e, per * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream);
             k_make_shoup<<<g, 256, 0, c->stream>>>(d_q, nullptr, p->d_s, total, 1, 1, c->dev);
         }
-        c->launches++;
+        launched(c, "k_make_shoup");
         if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = fail(FHE_ERR_CUDA, "scale table kernel failed");
     }
     cudaFree(d_e);
@@ -1101,7 +1162,7 @@ static int launch_dct_pointwise(fhe_ctx *c, const fhe_dct_plan *plan, u64 *data,
     if (int rc = make_ct_tensor_map(&tm, data, n_ct, k, n)) return rc;
     if (int rc = set_smem(k_dct_pointwise, DCT_SMEM)) return rc;
     k_dct_pointwise<<<(unsigned)grid, 256, DCT_SMEM, st>>>(tm, plan->d_c, plan->d_s, c->dev, nunits, upc, blk_stride);
-    c->launches++;
+    launched(c, "k_dct_pointwise");
     CU_TRY(cudaGetLastError());
     return FHE_OK;
 }
@@ -1195,7 +1256,7 @@ int fhe_fill_uniform(fhe_ctx *c, uint64_t *d_dst, uint64_t first_ct, uint64_t n_
     const unsigned long long total = (unsigned long long)n_ct * size * c->host.k * c->host.n;
     if (!total) return FHE_OK;
     k_fill_uniform<<<grid_for(total, 256, c->sm_count), 256, 0, c->stream>>>((u64 *)d_dst, first_ct, total, size, seed, c->dev);
-    c->launches++;
+    launched(c, "k_fill_uniform");
     CU_TRY(cudaGetLastError());
     return FHE_OK;
 }
@@ -1207,7 +1268,7 @@ int fhe_checksum(fhe_ctx *c, const uint64_t *d, uint64_t count, uint64_t *out)
     CU_TRY(cudaMemsetAsync(c->d_scratch, 0, 8, c->stream));
     if (count) {
         k_checksum<<<grid_for(count, 256, c->sm_count), 256, 0, c->stream>>>((const u64 *)d, count, c->d_scratch);
-        c->launches++;
+        launched(c, "k_checksum");
     }
     unsigned long long h = 0;
     CU_TRY(cudaMemcpyAsync(&h, c->d_scratch, 8, cudaMemcpyDeviceToHost, c->stream));

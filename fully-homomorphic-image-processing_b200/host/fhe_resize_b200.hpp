@@ -1,31 +1,33 @@
-// fhe_resize_b200.hpp -- the resize image-op library of the reference (homo/fhe_resize.h) on B200.
+// fhe_resize_b200.hpp -- the pixel loop of the reference's resize server (homo/fhe_resize.h:308-392:
+// ResizeImage over SampleBicubic / SampleLinear over Cubic / Linear) as a B200-first row engine.
 //
-// Same call surface as the reference, evaluated through seal_b200::Evaluator on the device:
+// The reference's own op graphs are NOT restated here: homo/fhe_resize.h compiles unchanged against
+// include/seal/seal.h and runs op by op on the GPU (oracle/Makefile `ref`,
+// tests/test_reference_sources_on_gpu.py).  This header is the fast path a server uses instead:
 //
-//   Cubic  (result, A, B, C, D, t, evaluator, encoder, encryptor)      homo/fhe_resize.h:143-189
-//   Linear (result, A, B, t, evaluator, encoder, encryptor)            homo/fhe_resize.h:191-204
-//   SImageData, GetPixelClamped                                       homo/fhe_resize.h:207-220
-//   SampleLinear / SampleBicubic (ret, image, x, y, ...)              homo/fhe_resize.h:222-305
-//   ResizeImage (source, ow, oh, destImage, dw, dh, inter, ...)       homo/fhe_resize.h:308-392
+//   * one output ROW at a time: the 15 Cubic (9 Linear) calls of every output pixel become five
+//     (three) calls of the fused device graphs fhe_cubic / fhe_linear (include/fhe_b200.h), each over
+//     the whole row x 3 channels, reading the 4 x 4 (2 x 2) neighbourhoods through pointer tables;
+//   * the powers of the fractions are formed once and kept as operand forms: square(t) and
+//     multiply(t, t) are functions of t alone (and the same ciphertext: fhe_resize.h:174-175), the
+//     three channels of a pixel share them, and with a deterministic Encryptor (the key-less
+//     transparent one) the x fractions do not depend on the row and the y fraction not on the column;
+//   * with a deterministic Encryptor the horizontal pass of a SOURCE row is the same ciphertext for
+//     every output row that touches it, so it is computed once per source row (two output rows share
+//     it at a 2x reduction);
+//   * source rows stream in and output rows stream out (RowSource / RowSink): device memory holds a
+//     window, not the image -- 512 x 512 x 3 ciphertexts of n = 8192 are 384 GiB.
 //
-// The graphs are the reference's own, op for op, INCLUDING its quirks:
-// Cubic's `t3` is t*t, not t^3 (:175); u = x / (dw - 1) * ow - 0.5 and int() truncation toward
-// zero for the integer part with floor() for the fraction (:228-234, :351, :382); the fractions are
-// encrypted on the server (:230-266) -- through whatever seal_b200::Encryptor the caller passes.
-// ct x ct products grow the ciphertexts (no relinearisation in the reference): size 4 after the
-// first Cubic level, size 6 after the second; sizes 3 / 4 for Linear.
-// Like the reference, Cubic and Linear print their wall time in ms followed by ',' to stdout.
-//
-// The only departure is the ciphertext SOURCE of ResizeImage: the reference reads
-// seal::Ciphertext::load from a file stream (:313-342); here a callable yields the next ciphertext
-// of the RGB-interleaved row-major stream (client_resize.cpp:141-154), so the caller chooses the
-// wire format (a raw u64 reader is provided; SEAL's own serialisation is SURVEY.md 8f-N2).
+// Every ciphertext produced equals the reference's bit for bit (tests/cpp/test_resize_decode.cpp
+// against the oracle's op-by-op graph; with a callback Encryptor the encryptions are drawn in the
+// reference's order, x then y per output pixel, and nothing is shared across pixels).
+// The coordinates follow fhe_resize.h:351,382 (float arithmetic, int() truncation, floor() for the
+// fraction, clamped neighbourhoods :215-220).
 #pragma once
 #include <algorithm>
-#include <chrono>
 #include <cmath>
 #include <fstream>
-#include <iostream>
+#include <map>
 #include <string>
 
 #include "seal_b200.hpp"
@@ -35,178 +37,36 @@ namespace seal_b200 {
 constexpr int BILINEAR = 0;  // fhe_resize.h:14
 constexpr int BICUBIC = 1;   // fhe_resize.h:15
 
-namespace detail {
-// The bodies of Cubic and Linear, written once for any ciphertext type the Evaluator overloads
-// (one seal-style Ciphertext, or a CiphertextBatch = the same graph on a whole row of pixels).
-// fhe_resize.h:174-175: t2 = square(t); "t3" = multiply(t, t) (sic: t*t, not t^3)
-template <class CT>
-inline void cubic_powers(const CT &t, CT &t2, CT &t3, Evaluator &evaluator)
-{
-    t2 = t;
-    evaluator.square(t2);
-    t3 = t;
-    evaluator.multiply(t3, t);
-}
-template <class CT>
-inline void cubic_body(CT &result, CT &A, CT &B, CT &C, CT &D, CT &t, Evaluator &evaluator, FractionalEncoder &encoder,
-                       const std::pair<CT, CT> *powers = nullptr)
-{
-    CT a, b, c, d;
-    CT boaz1(A);
-    CT boaz2(B); evaluator.multiply_plain(boaz2, encoder.encode(3));
-    evaluator.sub(boaz2, boaz1);
-    CT boaz3(C); evaluator.multiply_plain(boaz3, encoder.encode(3));
-    evaluator.sub(boaz2, boaz3);
-    CT boaz4(D);
-    evaluator.add(boaz2, boaz4);
-    a = boaz2;
-
-    CT boaz5(A); evaluator.multiply_plain(boaz5, encoder.encode(2));
-    CT boaz6(B); evaluator.multiply_plain(boaz6, encoder.encode(5));
-    evaluator.sub(boaz5, boaz6);
-    CT boaz7(C); evaluator.multiply_plain(boaz7, encoder.encode(4));
-    evaluator.add(boaz5, boaz7);
-    CT boaz8(D);
-    evaluator.sub(boaz5, boaz8);
-    b = boaz5;
-
-    CT boaz9(A);
-    CT boaz10(C);
-    evaluator.sub(boaz10, boaz9);
-    c = boaz10;
-
-    d = B;
-
-    CT t2, t3;
-    if (powers) {  // square(t) and t*t are functions of t alone: a caller may compute them once per t
-        t2 = powers->first;
-        t3 = powers->second;
-    } else {
-        cubic_powers(t, t2, t3, evaluator);
-    }
-
-    evaluator.multiply(a, t3);
-    evaluator.multiply(b, t2);
-    evaluator.multiply(c, t);
-
-    evaluator.add(a, b);
-    evaluator.add(a, c);
-    evaluator.multiply_plain(a, encoder.encode(0.5));
-    evaluator.add(a, d);
-    result = a;
-}
-template <class CT>
-inline void linear_body(CT &result, CT &A, CT &B, CT &t, Evaluator &evaluator, FractionalEncoder &encoder)
-{
-    CT boaz1(t); evaluator.negate(boaz1); evaluator.add_plain(boaz1, encoder.encode(1.0));
-    evaluator.multiply(boaz1, A);
-    CT boaz2(B); evaluator.multiply(boaz2, t);
-    evaluator.add(boaz1, boaz2);
-    result = boaz1;
-}
-struct CsvMs {  // the reference prints the wall time of each call in ms followed by ','
-    const Context &ctx;
-    std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
-    explicit CsvMs(const Context &c) : ctx(c) {}
-    ~CsvMs()
+// the five plaintexts of Cubic (fhe_resize.h:151-183) from the caller's encoder
+class ResizePlan {
+public:
+    ResizePlan(const Context &ctx, const FractionalEncoder &encoder)
     {
-        fhe_ctx_sync(ctx.handle());
-        auto diff = std::chrono::steady_clock::now() - start;
-        std::cout << std::chrono::duration<double, std::milli>(diff).count() << ',';
+        std::vector<uint64_t> plains;
+        for (double v : {3.0, 2.0, 5.0, 4.0, 0.5}) {
+            const Plaintext p = encoder.encode(v);
+            plains.insert(plains.end(), p.coeffs().begin(), p.coeffs().end());
+        }
+        check(fhe_resize_plan_create(ctx.handle(), plains.data(), &h_));
     }
-};
-}  // namespace detail
+    ~ResizePlan() { fhe_resize_plan_destroy(h_); }
+    ResizePlan(const ResizePlan &) = delete;
+    ResizePlan &operator=(const ResizePlan &) = delete;
+    const fhe_resize_plan *handle() const { return h_; }
 
-inline void Cubic(Ciphertext &result, Ciphertext &A, Ciphertext &B, Ciphertext &C, Ciphertext &D, Ciphertext &t,
-                  Evaluator &evaluator, FractionalEncoder &encoder, Encryptor &encryptor)
-{
-    (void)encryptor;
-    detail::CsvMs timer(evaluator.context());
-    detail::cubic_body(result, A, B, C, D, t, evaluator, encoder);
-}
-inline void Linear(Ciphertext &result, Ciphertext &A, Ciphertext &B, Ciphertext &t, Evaluator &evaluator,
-                   FractionalEncoder &encoder, Encryptor &encryptor)
-{
-    (void)encryptor;
-    detail::CsvMs timer(evaluator.context());
-    detail::linear_body(result, A, B, t, evaluator, encoder);
-}
-// the same graphs on `count` independent inputs at once (no timing output: not a reference call)
-inline void Cubic(CiphertextBatch &result, CiphertextBatch &A, CiphertextBatch &B, CiphertextBatch &C, CiphertextBatch &D,
-                  CiphertextBatch &t, Evaluator &evaluator, FractionalEncoder &encoder,
-                  const std::pair<CiphertextBatch, CiphertextBatch> *powers = nullptr)
-{
-    detail::cubic_body(result, A, B, C, D, t, evaluator, encoder, powers);
-}
-inline void Linear(CiphertextBatch &result, CiphertextBatch &A, CiphertextBatch &B, CiphertextBatch &t, Evaluator &evaluator,
-                   FractionalEncoder &encoder)
-{
-    detail::linear_body(result, A, B, t, evaluator, encoder);
-}
-
-struct SImageData {
-    int width;
-    int height;
-    int start;
-    std::vector<std::vector<Ciphertext>> pixels;
+private:
+    fhe_resize_plan *h_ = nullptr;
 };
 
-inline std::vector<Ciphertext> GetPixelClamped(const SImageData &image, int x, int y)
-{
-    x = std::min(std::max(x, 0), image.width - 1);
-    y = std::min(std::max(y, 0), image.height - 1);
-    return image.pixels.at((size_t)(y * image.width + x - image.start));
-}
-
-inline void SampleLinear(std::vector<Ciphertext> &ret, const SImageData &image, float x, float y, Evaluator &evaluator,
-                         FractionalEncoder &encoder, Encryptor &encryptor)
-{
-    int xint = int(x);
-    Ciphertext xfract;
-    encryptor.encrypt(encoder.encode(x - std::floor(x)), xfract);
-    int yint = int(y);
-    Ciphertext yfract;
-    encryptor.encrypt(encoder.encode(y - std::floor(y)), yfract);
-
-    auto p00 = GetPixelClamped(image, xint + 0, yint + 0);
-    auto p10 = GetPixelClamped(image, xint + 1, yint + 0);
-    auto p01 = GetPixelClamped(image, xint + 0, yint + 1);
-    auto p11 = GetPixelClamped(image, xint + 1, yint + 1);
-
-    Ciphertext col0, col1;
-    for (int i = 0; i < 3; ++i) {
-        Linear(col0, p00[i], p10[i], xfract, evaluator, encoder, encryptor);
-        Linear(col1, p01[i], p11[i], xfract, evaluator, encoder, encryptor);
-        Linear(ret[i], col0, col1, yfract, evaluator, encoder, encryptor);
-    }
-}
-
-inline void SampleBicubic(std::vector<Ciphertext> &ret, const SImageData &image, float x, float y, Evaluator &evaluator,
-                          FractionalEncoder &encoder, Encryptor &encryptor)
-{
-    int xint = int(x);
-    Ciphertext xfract;
-    encryptor.encrypt(encoder.encode(x - std::floor(x)), xfract);
-    int yint = int(y);
-    Ciphertext yfract;
-    encryptor.encrypt(encoder.encode(y - std::floor(y)), yfract);
-
-    std::vector<Ciphertext> p[4][4];  // p[column offset][row offset]
-    for (int r = 0; r < 4; ++r)
-        for (int c = 0; c < 4; ++c) p[c][r] = GetPixelClamped(image, xint - 1 + c, yint - 1 + r);
-
-    Ciphertext col0, col1, col2, col3;
-    for (int i = 0; i < 3; ++i) {
-        Cubic(col0, p[0][0][i], p[1][0][i], p[2][0][i], p[3][0][i], xfract, evaluator, encoder, encryptor);
-        Cubic(col1, p[0][1][i], p[1][1][i], p[2][1][i], p[3][1][i], xfract, evaluator, encoder, encryptor);
-        Cubic(col2, p[0][2][i], p[1][2][i], p[2][2][i], p[3][2][i], xfract, evaluator, encoder, encryptor);
-        Cubic(col3, p[0][3][i], p[1][3][i], p[2][3][i], p[3][3][i], xfract, evaluator, encoder, encryptor);
-        Cubic(ret[i], col0, col1, col2, col3, yfract, evaluator, encoder, encryptor);
-    }
-}
-
-// next ciphertext of the input stream (replaces `c.load(infile)`, fhe_resize.h:333-338)
+// next ciphertext of the input stream (what `c.load(infile)` yields, fhe_resize.h:333-338)
 using CiphertextSource = std::function<void(Ciphertext &)>;
+// Source row y of the RGB-interleaved row-major stream (client_resize.cpp:141-154): returns the row's
+// original_width * 3 size-2 ciphertexts when `needed` (a fresh batch, or a slice of storage the caller
+// keeps resident), skips the row of the stream otherwise.  Rows are requested in increasing order,
+// each once.
+using RowSource = std::function<CiphertextBatch(int y, bool needed)>;
+// Output row y: dest_width * 3 ciphertexts (size 6 bicubic, 4 bilinear), RGB per pixel
+using RowSink = std::function<void(int y, CiphertextBatch &row)>;
 
 // raw reader: each ciphertext is 2*k*n little-endian u64 in [poly][limb][n] order, no framing
 inline CiphertextSource raw_file_source(const Context &ctx, const std::string &path)
@@ -223,182 +83,192 @@ inline CiphertextSource raw_file_source(const Context &ctx, const std::string &p
         dst = std::move(x);
     };
 }
-
-inline void ResizeImage(const CiphertextSource &load, int original_width, int original_height, SImageData &destImage,
-                        int dest_width, int dest_height, int inter, Evaluator &evaluator, FractionalEncoder &encoder,
-                        Encryptor &encryptor)
+// a RowSource over a ciphertext-at-a-time source
+inline RowSource rows_of(const CiphertextSource &load, int original_width)
 {
-    SImageData srcImage;
-    srcImage.width = original_width;
-    srcImage.height = original_height;
-    srcImage.start = 0;
-
-    int init_rows = 0;
-    Ciphertext c;
-    if (inter == BILINEAR) init_rows = 2;
-    else if (inter == BICUBIC) init_rows = 4;
-    else throw std::invalid_argument("unknown interpolation");
-    auto load_pixel = [&]() {
-        std::vector<Ciphertext> pixel;
-        for (int j = 0; j < 3; ++j) {
+    return [load, original_width](int, bool needed) {
+        Ciphertext c;
+        CiphertextBatch row;
+        for (int i = 0; i < original_width * 3; ++i) {
             load(c);
-            pixel.push_back(c);
+            if (needed && i == 0) row = CiphertextBatch(*c.context(), (size_t)original_width * 3, 2);
+            if (needed) row.set((size_t)i, c);
         }
-        return pixel;
+        return row;
     };
-    for (int i = 0; i < original_width * init_rows; i++) srcImage.pixels.push_back(load_pixel());
+}
 
-    destImage.width = dest_width;
-    destImage.height = dest_height;
-    destImage.start = 0;
-    destImage.pixels.clear();
-
-    for (int y = 0; y < destImage.height; ++y) {
-        float v = float(y) / float(destImage.height - 1) * float(srcImage.height) - 0.5;
-        int new_start = std::min(int(v) - init_rows / 2 + 1, srcImage.height - init_rows) * srcImage.width;
-        if (new_start > srcImage.start) {
-            for (int i = srcImage.start + init_rows * srcImage.width; i < new_start; i++)
-                for (int j = 0; j < 3; j++) load(c);  // rows skipped entirely
-            std::vector<std::vector<Ciphertext>> new_pixels;
-            int present = 0;
-            for (int i = new_start - srcImage.start; i < init_rows * srcImage.width; i++) {
-                new_pixels.push_back(std::move(srcImage.pixels[(size_t)i]));
-                present++;
-            }
-            for (int i = present; i < init_rows * srcImage.width; i++) new_pixels.push_back(load_pixel());
-            srcImage.start = new_start;
-            srcImage.pixels = std::move(new_pixels);
-        }
-        for (int x = 0; x < destImage.width; ++x) {
-            float u = float(x) / float(destImage.width - 1) * float(srcImage.width) - 0.5;
-            std::vector<Ciphertext> sample(3);
-            if (inter == BILINEAR) SampleLinear(sample, srcImage, u, v, evaluator, encoder, encryptor);
-            else SampleBicubic(sample, srcImage, u, v, evaluator, encoder, encryptor);
-            destImage.pixels.push_back(std::move(sample));
-        }
+class RowResizer {
+public:
+    RowResizer(Evaluator &evaluator, FractionalEncoder &encoder, Encryptor &encryptor, int original_width, int original_height,
+               int dest_width, int dest_height, int inter)
+        : ev_(evaluator), enc_(encoder), cr_(encryptor), ctx_(evaluator.context()), ow_(original_width), oh_(original_height),
+          dw_(dest_width), dh_(dest_height), inter_(inter), taps_(inter == BICUBIC ? 4 : 2), off_(inter == BICUBIC ? -1 : 0)
+    {
+        if (inter != BILINEAR && inter != BICUBIC) throw std::invalid_argument("unknown interpolation");
+        if (ow_ < 1 || oh_ < 1 || dw_ < 1 || dh_ < 1) throw std::invalid_argument("bad image size");
+        if (evaluator.relinearization())
+            throw std::invalid_argument("the fused resize graphs follow the reference, which never relinearises");
+        if (inter == BICUBIC) plan_ = std::make_unique<ResizePlan>(ctx_, encoder);
     }
-}
 
-// the reference's signature: reads the raw stream from a file
-inline void ResizeImage(const std::string &infile_str, int original_width, int original_height, SImageData &destImage,
-                        int dest_width, int dest_height, int inter, Evaluator &evaluator, FractionalEncoder &encoder,
-                        Encryptor &encryptor)
-{
-    ResizeImage(raw_file_source(evaluator.context(), infile_str), original_width, original_height, destImage, dest_width,
-                dest_height, inter, evaluator, encoder, encryptor);
-}
+    // output rows [y_begin, y_end) (a band: ranks of a multi-GPU run take disjoint bands and feed each
+    // the source rows it touches)
+    void run(const RowSource &source, const RowSink &sink, int y_begin = 0, int y_end = -1)
+    {
+        if (y_end < 0) y_end = dh_;
+        const size_t count = (size_t)dw_ * 3;
+        const bool det = cr_.deterministic();
+        std::vector<int> xint((size_t)dw_);
+        std::vector<double> xfr((size_t)dw_);
+        for (int x = 0; x < dw_; ++x) {
+            const float u = float(x) / float(dw_ - 1) * float(ow_) - 0.5;
+            xint[(size_t)x] = int(u);
+            xfr[(size_t)x] = u - std::floor(u);
+        }
+        Fraction fx;  // the x fractions of a row: shared by all rows when the Encryptor is deterministic
+        if (det) {
+            CiphertextBatch xf(ctx_, (size_t)dw_, 2);
+            Ciphertext c;
+            for (int x = 0; x < dw_; ++x) {
+                cr_.encrypt(enc_.encode(xfr[(size_t)x]), c);
+                xf.set((size_t)x, c);
+            }
+            fx = fraction(xf);
+        }
+        int next_src = 0;
+        for (int y = y_begin; y < y_end; ++y) {
+            const float v = float(y) / float(dh_ - 1) * float(oh_) - 0.5;
+            const int yint = int(v);
+            const double yfr = v - std::floor(v);
+            int rows[4] = {0, 0, 0, 0};
+            for (int r = 0; r < taps_; ++r) rows[r] = std::min(std::max(yint + off_ + r, 0), oh_ - 1);
+            // window: drop what no later row needs, load what this row needs
+            const int lowest = *std::min_element(rows, rows + taps_);
+            for (auto it = src_.begin(); it != src_.end();) it = it->first < lowest ? src_.erase(it) : std::next(it);
+            for (auto it = hor_.begin(); it != hor_.end();) it = it->first < lowest ? hor_.erase(it) : std::next(it);
+            for (int r = 0; r < taps_; ++r) {
+                while (next_src <= rows[r]) {
+                    bool needed = false;
+                    for (int q = 0; q < taps_; ++q) needed |= rows[q] == next_src;
+                    CiphertextBatch row = source(next_src, needed);
+                    if (needed) {
+                        if (!row.valid() || row.count() != (size_t)ow_ * 3 || row.size() != 2) throw std::invalid_argument("source row has the wrong shape");
+                        src_.emplace(next_src, std::move(row));
+                    }
+                    ++next_src;
+                }
+                if (!src_.count(rows[r])) throw std::logic_error("source row left the window (bands must be fed from their first row)");
+            }
+            Fraction fy;
+            if (!det) {  // the reference's order: x then y for every output pixel (fhe_resize.h:230-234)
+                CiphertextBatch xf(ctx_, (size_t)dw_, 2), yf(ctx_, (size_t)dw_, 2);
+                Ciphertext c;
+                for (int x = 0; x < dw_; ++x) {
+                    cr_.encrypt(enc_.encode(xfr[(size_t)x]), c);
+                    xf.set((size_t)x, c);
+                    cr_.encrypt(enc_.encode(yfr), c);
+                    yf.set((size_t)x, c);
+                }
+                fx = fraction(xf);
+                fy = fraction(yf);
+                hor_.clear();
+            } else {
+                CiphertextBatch yf(ctx_, 1, 2);
+                Ciphertext c;
+                cr_.encrypt(enc_.encode(yfr), c);
+                yf.set(0, c);
+                fy = fraction(yf);
+            }
+            // horizontal pass of every source row this output row touches
+            for (int r = 0; r < taps_; ++r) {
+                if (hor_.count(rows[r])) continue;
+                const CiphertextBatch &row = src_.at(rows[r]);
+                std::vector<const uint64_t *> tp(count * (size_t)taps_);
+                for (int x = 0; x < dw_; ++x)
+                    for (int c = 0; c < taps_; ++c) {
+                        const int px = std::min(std::max(xint[(size_t)x] + off_ + c, 0), ow_ - 1);
+                        for (int ch = 0; ch < 3; ++ch) tp[((size_t)x * 3 + ch) * taps_ + c] = row.element((size_t)px * 3 + ch);
+                    }
+                hor_.emplace(rows[r], graph(tp, 2, fx, 3, count));
+            }
+            // vertical pass
+            std::vector<const uint64_t *> tp(count * (size_t)taps_);
+            for (size_t e = 0; e < count; ++e)
+                for (int r = 0; r < taps_; ++r) tp[e * taps_ + r] = hor_.at(rows[r]).element(e);
+            CiphertextBatch out = graph(tp, hor_.begin()->second.size(), fy, det ? (uint32_t)count : 3u, count);
+            sink(y, out);
+        }
+        src_.clear();
+        hor_.clear();
+    }
 
-// ---------------------------------------------------------------------------------------------
-// B200-first variant of ResizeImage + SampleBicubic / SampleLinear: identical arithmetic and
-// identical results (tests/cpp/test_resize_decode.cpp compares them ciphertext by ciphertext), but
-// one output ROW is sampled at a time: the 16 (4) neighbour pixels of every output pixel and
-// channel are gathered into CiphertextBatches of dest_width * 3 elements and each Evaluator call of
-// the Cubic / Linear graph covers the whole row.  The two fractions are encrypted once per output
-// pixel, in the reference's call order (x then y), and shared by the three channels.
+private:
+    // a batch of encrypted fractions with everything the graphs multiply by, as operand forms
+    struct Fraction {
+        std::shared_ptr<OperandForm> t, t2, one_minus_t;
+    };
+    Fraction fraction(const CiphertextBatch &t)
+    {
+        Fraction f;
+        f.t = std::make_shared<OperandForm>(ctx_, t);
+        if (inter_ == BICUBIC) {
+            // t2 = square(t); "t3" = multiply(t, t) (fhe_resize.h:174-175) is the same ciphertext
+            CiphertextBatch t2(ctx_, t.count(), 3);
+            check(fhe_multiply_form(ctx_.handle(), f.t->handle(), 1, f.t->handle(), 1, t2.device_data(), t.count()));
+            f.t2 = std::make_shared<OperandForm>(ctx_, t2);
+        } else {
+            CiphertextBatch m(t);  // 1 - t: negate, add_plain(encode(1.0)) (fhe_resize.h:196)
+            ev_.negate(m);
+            ev_.add_plain(m, enc_.encode(1.0));
+            f.one_minus_t = std::make_shared<OperandForm>(ctx_, m);
+        }
+        return f;
+    }
+    CiphertextBatch graph(const std::vector<const uint64_t *> &taps, uint32_t size_in, const Fraction &f, uint32_t t_div, size_t n_ct)
+    {
+        CiphertextBatch dest(ctx_, n_ct, size_in + (inter_ == BICUBIC ? 2u : 1u));
+        if (inter_ == BICUBIC)
+            check(fhe_cubic(ctx_.handle(), plan_->handle(), taps.data(), size_in, f.t->handle(), f.t2->handle(), f.t2->handle(), t_div,
+                            dest.device_data(), n_ct));
+        else
+            check(fhe_linear(ctx_.handle(), taps.data(), size_in, f.one_minus_t->handle(), f.t->handle(), t_div, dest.device_data(), n_ct));
+        return dest;
+    }
+
+    Evaluator &ev_;
+    FractionalEncoder &enc_;
+    Encryptor &cr_;
+    const Context &ctx_;
+    int ow_, oh_, dw_, dh_, inter_, taps_, off_;
+    std::unique_ptr<ResizePlan> plan_;
+    std::map<int, CiphertextBatch> src_, hor_;  // source rows in the window; their horizontal passes
+};
+
+struct SImageData {  // fhe_resize.h:207-213
+    int width;
+    int height;
+    int start;
+    std::vector<std::vector<Ciphertext>> pixels;
+};
+
+// ResizeImage's signature over the row engine, for images that fit in device memory
 inline void ResizeImageBatched(const CiphertextSource &load, int original_width, int original_height, SImageData &destImage,
                                int dest_width, int dest_height, int inter, Evaluator &evaluator, FractionalEncoder &encoder,
                                Encryptor &encryptor)
 {
-    const Context &ctx = evaluator.context();
-    SImageData srcImage;
-    srcImage.width = original_width;
-    srcImage.height = original_height;
-    srcImage.start = 0;
-    const int init_rows = inter == BILINEAR ? 2 : 4, taps = init_rows;
-    if (inter != BILINEAR && inter != BICUBIC) throw std::invalid_argument("unknown interpolation");
-    Ciphertext c;
-    auto load_pixel = [&]() {
-        std::vector<Ciphertext> pixel;
-        for (int j = 0; j < 3; ++j) {
-            load(c);
-            pixel.push_back(c);
-        }
-        return pixel;
-    };
-    for (int i = 0; i < original_width * init_rows; i++) srcImage.pixels.push_back(load_pixel());
     destImage.width = dest_width;
     destImage.height = dest_height;
     destImage.start = 0;
     destImage.pixels.clear();
-    const size_t count = (size_t)dest_width * 3;
-    for (int y = 0; y < dest_height; ++y) {
-        float v = float(y) / float(dest_height - 1) * float(srcImage.height) - 0.5;
-        int new_start = std::min(int(v) - init_rows / 2 + 1, srcImage.height - init_rows) * srcImage.width;
-        if (new_start > srcImage.start) {
-            for (int i = srcImage.start + init_rows * srcImage.width; i < new_start; i++)
-                for (int j = 0; j < 3; j++) load(c);
-            std::vector<std::vector<Ciphertext>> new_pixels;
-            int present = 0;
-            for (int i = new_start - srcImage.start; i < init_rows * srcImage.width; i++) {
-                new_pixels.push_back(std::move(srcImage.pixels[(size_t)i]));
-                present++;
-            }
-            for (int i = present; i < init_rows * srcImage.width; i++) new_pixels.push_back(load_pixel());
-            srcImage.start = new_start;
-            srcImage.pixels = std::move(new_pixels);
-        }
-        // gather: tap[r][cidx] holds, for every (x, channel), the neighbour (xint + off + cidx, yint + off + r)
-        std::vector<std::vector<CiphertextBatch>> tap((size_t)taps, std::vector<CiphertextBatch>());
-        for (auto &row : tap)
-            for (int cidx = 0; cidx < taps; ++cidx) row.emplace_back(ctx, count, 2);
-        // one encrypted fraction pair per output pixel; the three channels share it
-        CiphertextBatch xf1(ctx, (size_t)dest_width, 2), yf1(ctx, (size_t)dest_width, 2);
-        const int off = inter == BICUBIC ? -1 : 0;
-        const int yint = int(v);
+    RowResizer rr(evaluator, encoder, encryptor, original_width, original_height, dest_width, dest_height, inter);
+    rr.run(rows_of(load, original_width), [&](int, CiphertextBatch &row) {
         for (int x = 0; x < dest_width; ++x) {
-            float u = float(x) / float(dest_width - 1) * float(srcImage.width) - 0.5;
-            const int xint = int(u);
-            Ciphertext xf, yf;
-            encryptor.encrypt(encoder.encode(u - std::floor(u)), xf);
-            encryptor.encrypt(encoder.encode(v - std::floor(v)), yf);
-            xf1.set((size_t)x, xf);
-            yf1.set((size_t)x, yf);
-            for (int r = 0; r < taps; ++r)
-                for (int cidx = 0; cidx < taps; ++cidx) {
-                    int px = std::min(std::max(xint + off + cidx, 0), srcImage.width - 1);
-                    int py = std::min(std::max(yint + off + r, 0), srcImage.height - 1);
-                    const std::vector<Ciphertext> &pixel = srcImage.pixels.at((size_t)(py * srcImage.width + px - srcImage.start));
-                    for (int ch = 0; ch < 3; ++ch) tap[(size_t)r][(size_t)cidx].set((size_t)x * 3 + ch, pixel[(size_t)ch]);
-                }
+            std::vector<Ciphertext> px;
+            for (int ch = 0; ch < 3; ++ch) px.push_back(row.get((size_t)x * 3 + ch));
+            destImage.pixels.push_back(std::move(px));
         }
-        auto per_channel = [&](const CiphertextBatch &one) {  // element x -> elements 3x, 3x+1, 3x+2
-            CiphertextBatch r(ctx, count, one.size());
-            const size_t w = ctx.ct_words(one.size()) * sizeof(uint64_t);
-            for (int ch = 0; ch < 3; ++ch)
-                check(fhe_device_copy_2d(ctx.handle(), r.device_data() + (size_t)ch * ctx.ct_words(one.size()), 3 * w,
-                                         one.device_data(), w, w, one.count()));
-            return r;
-        };
-        CiphertextBatch xfract = per_channel(xf1), yfract = per_channel(yf1);
-        CiphertextBatch out;
-        if (inter == BICUBIC) {
-            // the powers of the fractions are the same ciphertexts in every Cubic that uses them (4 rows x 3
-            // channels for x, 3 channels for y): computed once per output pixel, bit-identical
-            CiphertextBatch x2, x3, y2, y3;
-            detail::cubic_powers(xf1, x2, x3, evaluator);
-            detail::cubic_powers(yf1, y2, y3, evaluator);
-            const std::pair<CiphertextBatch, CiphertextBatch> xp(per_channel(x2), per_channel(x3)), yp(per_channel(y2), per_channel(y3));
-            std::vector<CiphertextBatch> col(4);
-            for (int r = 0; r < 4; ++r)
-                Cubic(col[(size_t)r], tap[(size_t)r][0], tap[(size_t)r][1], tap[(size_t)r][2], tap[(size_t)r][3], xfract, evaluator, encoder, &xp);
-            Cubic(out, col[0], col[1], col[2], col[3], yfract, evaluator, encoder, &yp);
-        } else {
-            CiphertextBatch col0, col1;
-            Linear(col0, tap[0][0], tap[0][1], xfract, evaluator, encoder);
-            Linear(col1, tap[1][0], tap[1][1], xfract, evaluator, encoder);
-            Linear(out, col0, col1, yfract, evaluator, encoder);
-        }
-        for (int x = 0; x < dest_width; ++x) {
-            std::vector<Ciphertext> sample;
-            for (int ch = 0; ch < 3; ++ch) sample.push_back(out.get((size_t)x * 3 + ch));
-            destImage.pixels.push_back(std::move(sample));
-        }
-        // Nothing above waits for the device, so the host could queue many rows ahead; the
-        // temporaries of every queued row would then be live in the stream-ordered pool at once
-        // (gigabytes at size 6) and the pool would keep growing through the driver.  One
-        // synchronisation per output row bounds that to a row's worth.
-        check(fhe_ctx_sync(ctx.handle()));
-    }
+    });
 }
 
 }  // namespace seal_b200

@@ -41,8 +41,9 @@ inline void check(int rc)
 // server_jpeg.cpp:76), coeff_modulus_128(n) unless a chain is given, plain_modulus t.
 class Context {
 public:
+    // cuda_stream: a cudaStream_t the context should work on (null: its own)
     explicit Context(uint32_t n, uint64_t plain_modulus = 1 << 14, std::vector<uint64_t> coeff_modulus = {},
-                     int device = 0)
+                     int device = 0, void *cuda_stream = nullptr)
         : n_(n), t_(plain_modulus), q_(std::move(coeff_modulus))
     {
         if (q_.empty()) {
@@ -51,7 +52,7 @@ public:
             check(fhe_default_coeff_modulus(n, buf, &k));
             q_.assign(buf, buf + k);
         }
-        check(fhe_ctx_create(n, (uint32_t)q_.size(), q_.data(), t_, device, nullptr, &h_));
+        check(fhe_ctx_create(n, (uint32_t)q_.size(), q_.data(), t_, device, cuda_stream, &h_));
     }
     ~Context() { fhe_ctx_destroy(h_); }
     Context(const Context &) = delete;
@@ -306,6 +307,30 @@ private:
     uint32_t size_ = 0;
 };
 
+// The operand half of Evaluator::multiply done once (include/fhe_b200.h fhe_form_create): the BEHZ
+// extension and the forward transforms of `count` ciphertexts.  Immutable; a graph that multiplies by
+// the same ciphertexts repeatedly (the powers of the fractions in Cubic, shifted_x in the Taylor
+// series) builds the form once and passes it to fhe_multiply_form / fhe_cubic / fhe_linear.
+class OperandForm {
+public:
+    OperandForm(const Context &ctx, const CiphertextBatch &b) : count_(b.count()), size_(b.size())
+    {
+        if (!b.valid() || b.context() != &ctx) throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        check(fhe_form_create(ctx.handle(), b.device_data(), b.size(), b.count(), &h_));
+    }
+    ~OperandForm() { fhe_form_destroy(h_); }
+    OperandForm(const OperandForm &) = delete;
+    OperandForm &operator=(const OperandForm &) = delete;
+    const fhe_form *handle() const { return h_; }
+    size_t count() const { return count_; }
+    uint32_t size() const { return size_; }
+
+private:
+    fhe_form *h_ = nullptr;
+    size_t count_;
+    uint32_t size_;
+};
+
 // seal::Encryptor.  fhe_image.h only passes it through; fhe_resize.h (:230-266) and fhe_decode.h
 // (:54,134) encrypt PUBLIC scalars on the server with it.  Two server-side forms:
 //   * Encryptor(fn): a callback that produces the ciphertext (a real public-key encryption made by
@@ -320,6 +345,8 @@ public:
     explicit Encryptor(Fn fn) : fn_(std::move(fn)) {}
     explicit Encryptor(const Context &ctx) : ctx_(&ctx) {}
     void encrypt(const Plaintext &plain, Ciphertext &destination) const;
+    // true: equal plaintexts give equal ciphertexts (the transparent form), so a graph may share them
+    bool deterministic() const { return !fn_ && ctx_; }
     // `count` fresh encryptions of the same plaintext (one callback invocation each)
     void encrypt(const Plaintext &plain, CiphertextBatch &destination, size_t count) const
     {
@@ -472,6 +499,17 @@ public:
         check(fhe_square(ctx_->handle(), a.device_data(), a.size(), dest.device_data(), a.count()));
         a = std::move(dest);
         if (auto_relin_) relinearize(a, *auto_relin_);
+    }
+    // product i = ciphertext i / a_div of `a` times ciphertext i / b_div of `b`, from operand forms
+    // (fhe_multiply_form): `n_ct` products (default: one per ciphertext of `a`); a form times itself is
+    // Evaluator::square.  Follows the relinearisation policy like multiply.
+    CiphertextBatch multiply(const OperandForm &a, const OperandForm &b, uint32_t a_div = 1, uint32_t b_div = 1, size_t n_ct = 0)
+    {
+        if (!n_ct) n_ct = a.count() * a_div;
+        CiphertextBatch dest(*ctx_, n_ct, a.size() + b.size() - 1);
+        check(fhe_multiply_form(ctx_->handle(), a.handle(), a_div, b.handle(), b_div, dest.device_data(), n_ct));
+        if (auto_relin_) relinearize(dest, *auto_relin_);
+        return dest;
     }
     void relinearize(CiphertextBatch &a, const EvaluationKeys &evk)
     {

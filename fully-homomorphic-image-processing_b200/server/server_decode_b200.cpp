@@ -31,7 +31,7 @@ int main(int argc, const char **argv)
     const cli_b200::Parsed opt = cli_b200::parse(argc, argv, spec);
     if (opt.has("help")) {
         std::printf("%s [-f in] [-o out] [--delta d] [--order o] [--degree g] [--ncoeff N] [--fcoeff N] [--cmod n] [--pmod t] "
-                    "[--base b] [-v]\n", argv[0]);
+                    "[--base b] [-v]\n  ciphertext stream layout: host/seal_wire_b200.hpp (SEAL 2.3 layout from recall, UNVERIFIED against real SEAL files)\n", argv[0]);
         return 0;
     }
     int pairs[3] = {0, 0, 0}, width = 0, height = 0;
@@ -72,7 +72,7 @@ int main(int argc, const char **argv)
                 std::vector<Ciphertext> run;
                 if (!load_ciphertext(myfile, context, elem, hdr) || !load_ciphertext(myfile, context, count, hdr))
                     throw std::invalid_argument("ciphertext stream ended early");
-                approximated_step(elem, index, count, order, degree, delta, width, height, run, evaluator, encoder, encryptor);
+                approximated_step_batched(elem, index, count, order, degree, delta, width, height, run, evaluator, encoder, encryptor);
                 for (int k = 0; k < width * height; k++) evaluator.add(channel[(size_t)k], run[(size_t)k]);
                 evaluator.add(index, count);
             }

@@ -8,11 +8,18 @@
 //   resized pixels, 3 ciphertexts each (size 6 bicubic / 4 bilinear), server_resize.cpp:141-146
 //   stdout: "Cubic,<ms>,<ms>,...\n" or "Linear,..." (server_resize.cpp:124-139)
 //
-// The op graph is ResizeImage / SampleBicubic / Cubic of homo/fhe_resize.h op for op, evaluated a
-// ROW of output pixels at a time on the device (ResizeImageBatched); `--per-pixel` runs the
-// reference's pixel-at-a-time order instead (same ciphertexts).  The public fractions are
-// encrypted with the key-less transparent Encryptor: this server loads neither the public key nor
-// the secret key the reference reads "FOR DEBUGGING ONLY" (server_resize.cpp:99-116).
+// The pixel loop runs on the row engine of host/fhe_resize_b200.hpp (RowResizer: fused Cubic / Linear
+// device graphs, fraction powers as operand forms, horizontal passes shared between output rows);
+// source rows stream in from the input file and output rows stream out, so device memory holds a
+// window of rows, not the image.  The ciphertexts written are the reference's bit for bit (its own
+// homo/server_resize.cpp compiles unchanged against include/seal/seal.h: oracle/_ref/server_resize;
+// tests compare both with the oracle).  The public fractions are encrypted with the key-less
+// transparent Encryptor: this server loads neither the public key nor the secret key the reference
+// reads "FOR DEBUGGING ONLY" (server_resize.cpp:99-116).
+// stdout: the label, then ONE measured value per output row -- the row's device + stream time in ms
+// divided by the Cubic / Linear calls the reference would have made for it (15 / 9 per pixel), repeated
+// once per such call so that benchmark/analyze.py's per-label mean stays a per-call time.  The values
+// are row averages, not individual call timings (the calls of a row run as five fused launches).
 #include <chrono>
 #include <cstdio>
 #include <fstream>
@@ -29,11 +36,11 @@ int main(int argc, const char **argv)
     cli_b200::Spec spec;
     spec.alias = {{"-f", "file"}, {"-o", "outfile"}, {"-v", "verbose"}, {"-w", "width"}, {"-h", "height"}};
     spec.valued = {"file", "outfile", "ncoeff", "fcoeff", "cmod", "pmod", "width", "height", "base"};
-    spec.switches = {"bicubic", "verbose", "help", "per-pixel"};
+    spec.switches = {"bicubic", "verbose", "help"};
     const cli_b200::Parsed opt = cli_b200::parse(argc, argv, spec);
     if (opt.has("help")) {
         std::printf("%s [-f in] [-o out] [--bicubic] -w W -h H [--ncoeff N] [--fcoeff N] [--cmod n] [--pmod t] [--base b] "
-                    "[--per-pixel] [-v]\n", argv[0]);
+                    "[-v]\n  ciphertext stream layout: host/seal_wire_b200.hpp (SEAL 2.3 layout from recall, UNVERIFIED against real SEAL files)\n", argv[0]);
         return 0;
     }
     int original_width = 0, original_height = 0, channels = 0;
@@ -66,27 +73,34 @@ int main(int argc, const char **argv)
             return 1;
         }
         WireHeader hdr;
-        CiphertextSource source = [&](Ciphertext &dst) {
-            if (!load_ciphertext(infile, context, dst, hdr)) throw std::invalid_argument("ciphertext stream ended early");
+        std::vector<uint64_t> host;
+        RowSource source = [&](int, bool needed) {
+            CiphertextBatch row;
+            if (needed) row = CiphertextBatch(context, (size_t)original_width * 3, 2);
+            for (int i = 0; i < original_width * 3; ++i) {
+                if (!load_ciphertext(infile, context, host, hdr)) throw std::invalid_argument("ciphertext stream ended early");
+                if (hdr.size != 2) throw std::invalid_argument("input ciphertexts must have size 2");
+                if (needed) check(fhe_upload(context.handle(), row.element((size_t)i), host.data(), host.size() * sizeof(uint64_t)));
+            }
+            return row;
         };
         std::cout << (bicubic ? "Cubic," : "Linear,");
-        SImageData resize_im;
         const int inter = bicubic ? BICUBIC : BILINEAR;
-        if (opt.has("per-pixel")) {
-            ResizeImage(source, original_width, original_height, resize_im, resized_width, resized_height, inter, evaluator,
-                        encoder, encryptor);  // Cubic / Linear print their own timings, like the reference
-        } else {
-            const auto t0 = std::chrono::steady_clock::now();
-            ResizeImageBatched(source, original_width, original_height, resize_im, resized_width, resized_height, inter,
-                               evaluator, encoder, encryptor);
+        const size_t calls_per_row = (size_t)resized_width * (bicubic ? 15 : 9);
+        RowResizer resizer(evaluator, encoder, encryptor, original_width, original_height, resized_width, resized_height, inter);
+        auto t0 = std::chrono::steady_clock::now();
+        std::vector<uint64_t> out;
+        resizer.run(source, [&](int, CiphertextBatch &row) {
             context.sync();
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            const size_t calls = (size_t)resized_width * resized_height * (bicubic ? 15 : 9);
-            for (size_t i = 0; i < calls; ++i) std::cout << ms / calls << ',';
-        }
+            for (size_t i = 0; i < calls_per_row; ++i) std::cout << ms / calls_per_row << ',';
+            out.resize(context.ct_words(row.size()) * row.count());
+            row.download(out.data());
+            for (size_t i = 0; i < row.count(); ++i)
+                save_ciphertext(outfile, context, out.data() + i * context.ct_words(row.size()), row.size(), hdr.hash);
+            t0 = std::chrono::steady_clock::now();
+        });
         std::cout << std::endl;
-        for (size_t i = 0; i < resize_im.pixels.size(); i++)
-            for (int j = 0; j < 3; j++) save_ciphertext(outfile, resize_im.pixels[i][(size_t)j], hdr.hash);
         return 0;
     } catch (const std::exception &e) {
         std::fprintf(stderr, "server_resize_b200: %s\n", e.what());

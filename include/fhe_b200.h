@@ -262,6 +262,16 @@ int fhe_set_dct_chunk_blocks(fhe_ctx *ctx, uint32_t blocks);
 int fhe_set_stage_timing(fhe_ctx *ctx, int enabled);
 int fhe_get_stage_times(fhe_ctx *ctx, float *ms /* 3 */);
 
+/* Per-kernel device time of everything this context launches between the two calls: an event is
+ * recorded after every kernel launch (a launch's time = the gap to the previous mark on the context's
+ * stream, so host-side gaps between launches are attributed to the kernel that follows them; use on
+ * warmed-up, GPU-bound sequences, outside timed regions).  fhe_profile_end waits for the stream and
+ * returns, per kernel name in order of first appearance: names as one '\n'-separated string, summed
+ * milliseconds and launch counts. */
+int fhe_profile_begin(fhe_ctx *ctx);
+int fhe_profile_end(fhe_ctx *ctx, char *names, size_t names_len, float *ms, uint64_t *counts,
+                    uint32_t max_kernels, uint32_t *n_out);
+
 #ifdef __cplusplus
 }
 #endif

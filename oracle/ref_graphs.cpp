@@ -8,9 +8,10 @@
 //       in : 192 size-2 ciphertexts R64 G64 B64 (server_jpeg.cpp:115-124), raw u64 [poly][limb][n]
 //       out: rgb_to_ycc_fhe per pixel, encrypted_dct per channel (server_jpeg.cpp:126-136), then
 //            quantize_fhe with YQT / UVQT / UVQT -- 192 ciphertexts
-//   ref_graphs resize <n> <ncoeff> <fcoeff> <in.bin> <out.bin> <stream.wire> <ow> <oh> <dw> <dh>
+//   ref_graphs resize <n> <ncoeff> <fcoeff> <in.bin> <out.bin> <stream.wire> <ow> <oh> <dw> <dh> [<evk.bin> <dbc>]
 //       in : A B C D t; out: Cubic level 1, Cubic level 2 (four copies of level 1), Linear, then the
-//            bicubic ResizeImage of the wire-format stream (fhe_resize.h:308-392 reads the file itself)
+//            bicubic ResizeImage of the wire-format stream (fhe_resize.h:308-392 reads the file itself);
+//            with keys: Cubic and Linear again with every product relinearised
 //   ref_graphs decode <n> <ncoeff> <fcoeff> <in.bin> <out.bin> <order> <degree> <delta> <npos> [<evk.bin> <dbc>]
 //       in : x_sin x_cos amplitude index count; out: homomorphic_sin, homomorphic_cos,
 //            approximated_step (npos x 1); with keys: the same three again with every product
@@ -111,6 +112,18 @@ int main(int argc, char **argv)
                         std::atoi(argv[11]), BICUBIC, evaluator, encoder, encryptor);
             for (auto &px : dest.pixels)
                 for (auto &ch : px) dump(ch);
+            if (argc > 13) {
+                const std::vector<uint64_t> kw = slurp(argv[12]);
+                EvaluationKeys evk;
+                evk.assign(context, kw.data(), std::atoi(argv[13]), 1);
+                evaluator.set_relinearization(&evk.device(dc));
+                Ciphertext cr, lr;
+                Cubic(cr, A, B, C, D, t, evaluator, encoder, encryptor);
+                dump(cr);
+                Linear(lr, A, B, t, evaluator, encoder, encryptor);
+                dump(lr);
+                evaluator.set_relinearization(nullptr);
+            }
         } else if (mode == "decode") {
             if (argc < 11) throw std::runtime_error("decode: missing arguments");
             const int order = std::atoi(argv[7]), degree = std::atoi(argv[8]), npos = std::atoi(argv[10]);

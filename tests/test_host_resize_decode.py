@@ -1,8 +1,8 @@
-"""The C++ host layer for the resize / decode op libraries (host/fhe_resize_b200.hpp,
-host/fhe_decode_b200.hpp): the reference's Cubic / Linear / SampleBicubic / ResizeImage
-(homo/fhe_resize.h:143-392) and homomorphic_sin / cos / approximated_step (homo/fhe_decode.h:48-242)
-signatures over the C-ABI.  CPU: compiles and fails loudly without a device.  GPU: every result of
-tests/cpp/test_resize_decode.cpp equals the oracle's op-by-op graphs bit for bit."""
+"""The B200-first C++ host layer for the resize / decode servers (host/fhe_resize_b200.hpp: RowResizer
+over the fused Cubic / Linear device graphs; host/fhe_decode_b200.hpp: batched Taylor series and step
+approximation over operand forms).  CPU: compiles and fails loudly without a device.  GPU: every
+result of tests/cpp/test_resize_decode.cpp equals the oracle's op-by-op restatement of the reference's
+graphs (homo/fhe_resize.h:143-392, homo/fhe_decode.h:48-242) bit for bit."""
 import os
 import subprocess
 
@@ -235,20 +235,17 @@ def test_resize_decode_host_layer_matches_oracle_on_gpu(pkg, oracle_mod, tmp_pat
     want.append(tz)
     # Evaluator::set_relinearization: the same graphs with every product relinearised
     s_rl = sin_relin_oracle(o, ct(0), ct(8), evk, dbc)
-    lin_rl = linear_relin_oracle(o, ct(0), ct(1), ct(4), evk, dbc)
-    cub_rl = cubic_relin_oracle(o, ct(0), ct(1), ct(2), ct(3), ct(4), evk, dbc)
     step_rl = approximated_step_relin_oracle(o, ct(5), ct(6), ct(7), 8, 2, 0.25, 2, data[8 * W:16 * W].copy(), evk, dbc)
-    want += [s_rl, lin_rl, cub_rl, step_rl]
+    want += [s_rl, step_rl]
     want = np.concatenate(want)
     assert got.size == want.size
     assert (got == want).all()
-    # (1 - t) A + t B = 0.375 * 12 + 0.625 * 200
-    assert abs(o.decode(o.decrypt(sk, lin_rl, 2)) - 129.5) < 1e-6
+    # (1 - t) A + t B = 0.375 * 12 + 0.625 * 200: the size-3 result of the fused Linear decrypts
+    assert abs(o.decode(o.decrypt(sk, lin, 3)) - 129.5) < 1e-6
     if n == 8192:
         # four limbs carry both multiplicative levels of Cubic: the size-4 level-1 result decrypts to
         # ((a + b) t^2 + c t) / 2 + B of the plaintext mirror (t3 = t * t, fhe_resize.h:175)
         A, B, C, D, t = 12.0, 200.0, 131.0, 77.0, 0.625
         a, b, cc = -A + 3 * B - 3 * C + D, 2 * A - 5 * B + 4 * C - D, C - A
         assert abs(o.decode(o.decrypt(sk, c1, 4)) - ((a * t * t + b * t * t + cc * t) * 0.5 + B)) < 1e-6
-        assert abs(o.decode(o.decrypt(sk, cub_rl, 2)) - ((a * t * t + b * t * t + cc * t) * 0.5 + B)) < 1e-6
     assert abs(o.decode(o.decrypt(sk, tz, 2)) - 0.375) < 1e-9

@@ -16,7 +16,8 @@ import numpy as np
 import pytest
 
 from conftest import PKG_NAME, ROOT
-from test_host_resize_decode import approximated_step_relin_oracle, resize_bicubic_oracle, sincos_relin_oracle
+from test_host_resize_decode import (approximated_step_relin_oracle, cubic_relin_oracle, linear_relin_oracle,
+                                      resize_bicubic_oracle, sincos_relin_oracle)
 from test_server_jpeg import wire_load_all, wire_save
 
 REFDIR = os.path.join(ROOT, "oracle", "_ref")
@@ -95,12 +96,16 @@ def test_reference_fhe_resize_h_on_gpu_at_config3_parameters(pkg, oracle_mod, tm
     assert k == 4
     data = o.fill_uniform(0, 5, 2, 0xC0B1C)
     src = o.fill_uniform(100, ow * oh * 3, 2, 0xAB5)
-    fin, fout, fwire = str(tmp_path / "in.bin"), str(tmp_path / "out.bin"), str(tmp_path / "stream.wire")
+    sk, _ = o.keygen(5)
+    dbc = 30
+    evk = o.evk_gen(sk, dbc, 1, 41)
+    fin, fout, fwire, fkey = (str(tmp_path / f) for f in ("in.bin", "out.bin", "stream.wire", "evk.bin"))
     data.tofile(fin)
+    evk.tofile(fkey)
     with open(fwire, "wb") as f:
         for i in range(ow * oh * 3):
             wire_save(f, src[i * W:(i + 1) * W], 2, k, n)
-    r = subprocess.run([exe, "resize", str(n), "100", "100", fin, fout, fwire, str(ow), str(oh), str(dw), str(dh)],
+    r = subprocess.run([exe, "resize", str(n), "100", "100", fin, fout, fwire, str(ow), str(oh), str(dw), str(dh), fkey, str(dbc)],
                        capture_output=True, text=True, timeout=1800)
     assert r.returncode == 0 and r.stdout.startswith("PASS"), r.stdout + r.stderr
     got = np.fromfile(fout, dtype=np.uint64)
@@ -122,7 +127,10 @@ def test_reference_fhe_resize_h_on_gpu_at_config3_parameters(pkg, oracle_mod, tm
             fr += [transparent(o, float(u - np.floor(u))), transparent(o, float(v - np.floor(v)))]
     res, nf = resize_bicubic_oracle(o, src, ow, oh, dw, dh, np.concatenate(fr))
     assert nf == 2 * dw * dh
-    want = np.concatenate([c1, c2, lin, res])
+    # the same two graphs with every product relinearised (Evaluator::set_relinearization under the reference's code)
+    cub_rl = cubic_relin_oracle(o, ct(0), ct(1), ct(2), ct(3), ct(4), evk, dbc)
+    lin_rl = linear_relin_oracle(o, ct(0), ct(1), ct(4), evk, dbc)
+    want = np.concatenate([c1, c2, lin, res, cub_rl, lin_rl])
     assert got.size == want.size
     assert (got == want).all()
 
