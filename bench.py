@@ -1,16 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- encrypted 8x8 DCT + quantize throughput (blocks/s), BASELINE.json's metric.
+"""bench.py -- BASELINE.json's metric (encrypted 8x8 DCT + quantize blocks/s) and the two other
+hot-path configurations (bicubic resize, homomorphic run-length decode) on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm (CUDA path, C-ABI)
-  python bench.py --impl reference [--gpus N] [--steps K] ...    # CPU arm (oracle op-by-op graph)
-  torchrun ... bench.py --gpus N ...                             # one rank per GPU, weak scaling
+  python bench.py [--gpus N] [--steps K] [--warmup W]                 # headline: DCT+quantize (config 2)
+  python bench.py --workload resize|decode ...                        # configs 3 and 5, own JSON line
+  python bench.py --impl reference [--workload ...] ...               # CPU arm (oracle op-by-op graph)
+  torchrun ... bench.py --gpus N [--ingest scatter] ...               # one rank per GPU, weak scaling
 
-A "step" is one pass of the hot path (encrypted_dct + quantize_fhe, fhe_image.h:196-305) over one
+dct (default).  A "step" is one pass of encrypted_dct + quantize_fhe (fhe_image.h:196-305) over one
 resident chunk of synthetic ciphertext blocks of BASELINE config 2 (server_jpeg DCT+quantize,
 1024x1024 RGB = 49152 blocks, n=4096, k=2, t=2^14).  The 384 GiB image does not fit in HBM, so it
 is streamed as chunks of --blocks blocks (default 8192 = 1/6 of the image, 64 GiB in + 64 GiB
 out); inputs are generated on the device (seeded SplitMix64, uniform residues)
-before the timed region.  Prints ONE JSON line (rank 0).
+before the timed region.  The default line also carries short side measurements of the other two
+workloads (keys "config3_resize", "config5_decode"; --no-side skips them).
+resize.  A step is a band of --rows output rows of BASELINE config 3 (server_resize --bicubic,
+512x512 -> 256x256 RGB, n=8192, k=4) through the row engine of host/fhe_resize_b200.hpp.
+decode.  A step is one run-length pair of BASELINE config 5 (approximated_step, 64 positions, degree
+12, order 64, n=8192, every product relinearised at dbc 30) through host/fhe_decode_b200.hpp.
+Prints ONE JSON line (rank 0).
 """
 import argparse
 import importlib
@@ -145,6 +153,10 @@ def main():
     ap.add_argument("--blocks", type=int, default=8192, help="blocks per step per GPU (resident chunk)")
     ap.add_argument("--e2e-blocks", type=int, default=256, help="blocks per end-to-end step (host buffers)")
     ap.add_argument("--chunk", type=int, default=0, help="internal chunk blocks (0 = one chunk)")
+    ap.add_argument("--workload", default="dct", choices=["dct", "resize", "decode"],
+                    help="dct: BASELINE config 2 (headline); resize: config 3; decode: config 5")
+    ap.add_argument("--rows", type=int, default=8, help="resize: output rows per step per GPU")
+    ap.add_argument("--no-side", action="store_true", help="dct: skip the short resize / decode side measurements")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tile", action="store_true", help="skip the fused RGB-tile side measurement")
     args = ap.parse_args()
@@ -153,7 +165,12 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank, world)
+        if args.workload == "dct":
+            run_reference(args, rank, world)
+        elif rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_workloads
+            print(json.dumps(bench_workloads.reference_resize(args) if args.workload == "resize" else bench_workloads.reference_decode(args)))
         return
 
     import torch
@@ -169,6 +186,16 @@ def main():
 
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
+    if args.workload != "dct":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_workloads
+        run = bench_workloads.run_resize if args.workload == "resize" else bench_workloads.run_decode
+        line = run(args, rank, world, local_rank, torch, dist, stream, ClockSampler, measured_peaks())
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     ctx = pkg.Context(N_RING, None, T_PLAIN, device=local_rank, stream=stream.cuda_stream)
     enc = pkg.FractionalEncoder(N_RING, T_PLAIN)
     plan = pkg.DctPlan(ctx, enc, pkg.YQT)
@@ -335,6 +362,20 @@ def main():
                          f"(oracle, op-by-op reference graph); single thread: {v1:.2f} blocks/s",
                "single_thread_value": v1}
 
+    # ---- short side measurements of the other two hot-path configurations (their own full lines:
+    # --workload resize / decode); every rank runs them, like the headline
+    side = {}
+    plan.close()
+    ctx.close()
+    if not args.no_side:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_workloads
+        for key, fn in (("config3_resize", bench_workloads.run_resize), ("config5_decode", bench_workloads.run_decode)):
+            try:
+                side[key] = fn(args, rank, world, local_rank, torch, dist, stream, ClockSampler, measured_peaks(), short=True)
+            except SystemExit as e:
+                side[key] = {"error": str(e)}
+
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -348,10 +389,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ebytes, "d2h_bytes_per_step": ebytes,
                     "blocks_per_step": EB, "steps": e2e_steps},
             "roofline": roofline, "cpu_baseline": cpu, "server_jpeg_tile": tile_info,
-            "output_checksum_xor": hex(int(cs_t.item())), "parity_spot_check": parity,
+            "output_checksum_xor": hex(int(cs_t.item())), "parity_spot_check": parity, **side,
         }))
-    plan.close()
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

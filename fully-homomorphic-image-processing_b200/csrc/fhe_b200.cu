@@ -1020,8 +1020,9 @@ int fhe_ptab_create(fhe_ctx *c, const uint64_t *plain, uint32_t count, fhe_ptab 
         for (uint32_t i = 0; i < n && ok; ++i) {
             const uint64_t m = plain[(size_t)p * n + i];
             if (!m) continue;
-            if (m == 1) terms.push_back(i);
-            else if (m == c->host.t - 1) terms.push_back(i | 0x80000000u);
+            // t - 1 is the lift of -1 (for t = 2 it coincides with 1 and is negative: m >= plain_thr)
+            if (m == c->host.t - 1) terms.push_back(i | 0x80000000u);
+            else if (m == 1) terms.push_back(i);
             else ok = false;
             if (terms.size() > (size_t)SPARSE_MAX) ok = false;
         }

@@ -41,7 +41,7 @@ struct DctPlan {
 
 inline fhe_dct_plan *dct_plan(Evaluator &ev, FractionalEncoder &enc, const std::vector<double> *quant)
 {
-    std::string key = "dct";
+    std::string key = "dct:" + enc.key() + ":";  // the tables are encodings: another encoder, another plan
     if (quant) key.append((const char *)quant->data(), quant->size() * sizeof(double));
     std::shared_ptr<void> &slot = ev.plan_slot(key);
     if (!slot) {

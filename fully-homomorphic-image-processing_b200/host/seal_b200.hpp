@@ -105,6 +105,11 @@ public:
         check(fhe_frac_encode(n_, t_, value, ic_, fc_, base_, c.data()));
         return Plaintext(std::move(c));
     }
+    // everything an encoding depends on besides the value (cache keys of pre-transformed plaintext sets)
+    std::string key() const
+    {
+        return std::to_string(n_) + "/" + std::to_string(t_) + "/" + std::to_string(ic_) + "/" + std::to_string(fc_) + "/" + std::to_string(base_);
+    }
 
 private:
     uint32_t n_;

@@ -41,7 +41,8 @@ static const double kColor[9] = {0.299, 0.587, 0.114, -0.168736, 0.331264, 0.5, 
 static void usage(const char *argv0)
 {
     std::printf("%s [-f|--file in] [-o|--outfile out] [--ncoeff N] [--fcoeff N] [--cmod n] [--pmod t] [--base b]\n"
-                "        [--quantize] [--chunk tiles] [-v|--verbose] [--help]\n", argv0);
+                "        [--quantize] [--chunk tiles] [-v|--verbose] [--help]\n"
+                "  ciphertext stream layout: host/seal_wire_b200.hpp (SEAL 2.3 layout from recall, UNVERIFIED against real SEAL files)\n", argv0);
 }
 
 int main(int argc, const char **argv)
@@ -136,16 +137,34 @@ int main(int argc, const char **argv)
             }
             const auto s0 = std::chrono::steady_clock::now();
             check(fhe_upload(context.handle(), dbuf, h, (size_t)nt * tile_words * 8));
+            check(fhe_profile_begin(context.handle()));
             check(fhe_jpeg_rgb_tiles(context.handle(), plan, (const uint64_t *)dbuf, (uint64_t *)dbuf, (uint64_t)nt));
+            // CSV contract (benchmark/analyze.py: per-label mean of the values): MEASURED device times of this
+            // chunk's kernels -- RGBYCC: the colour-conversion pass per pixel; DCT: forward transforms +
+            // pointwise DCT (+quantize) + inverse transforms per channel block (the transforms serve both
+            // steps and are counted under DCT).  Chunk averages, copies excluded (-v prints the wall time).
+            char names[512];
+            float kms[16];
+            uint64_t kcount[16];
+            uint32_t nk = 0;
+            check(fhe_profile_end(context.handle(), names, sizeof names, kms, kcount, 16, &nk));
+            double color_ms = 0, dct_ms = 0;
+            {
+                const char *p = names;
+                for (uint32_t i = 0; i < nk; ++i) {
+                    const char *e = std::strchr(p, '\n');
+                    const std::string name(p, e ? (size_t)(e - p) : std::strlen(p));
+                    (name == "k_rgb2ycc_ntt" ? color_ms : dct_ms) += kms[i];
+                    p = e ? e + 1 : p + name.size();
+                }
+            }
             check(fhe_download(context.handle(), h, dbuf, (size_t)nt * tile_words * 8));
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count();
-            // CSV contract: the colour conversion is ~1/6 of the fused multiplications of a tile
-            const double per_tile = ms / nt, color_ms = per_tile / 6.0, dct_ms = per_tile - color_ms;
             for (int t = 0; t < nt; ++t) {
                 std::cout << "RGBYCC,";
-                for (int i = 0; i < 64; ++i) std::cout << color_ms / 64 << ',';
+                for (int i = 0; i < 64; ++i) std::cout << color_ms / (64.0 * nt) << ',';
                 std::cout << std::endl << "DCT,";
-                for (int i = 0; i < 3; ++i) std::cout << dct_ms / 3 << ',';
+                for (int i = 0; i < 3; ++i) std::cout << dct_ms / (3.0 * nt) << ',';
                 std::cout << std::endl;
             }
             for (size_t i = 0; i < (size_t)nt * 192; ++i) save_ciphertext(outfile, context, h + i * W, 2, hdr.hash);

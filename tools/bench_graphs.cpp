@@ -50,6 +50,8 @@ struct DecodeBench {
     Ciphertext amplitude, index, count;
     int npos, degree, order;
     uint32_t out_size = 0;
+    bool host_mode = false;
+    uint64_t *h_in = nullptr, *h_out = nullptr;
 };
 
 // source rows a band touches: taps of its first and last output row (fhe_resize.h:351, clamped)
@@ -108,9 +110,9 @@ void *bres_create(int device, void *stream, uint32_t n, int ow, int oh, int dw, 
     }
 }
 
-// one step: the whole band.  checksum: order-sensitive checksum of every output row (device mode: of
-// the device rows; host mode: of the rows as they arrived in host memory, first word of each row only
-// hashed on the host to keep the timed region free of CPU work).
+// one step: the whole band.  checksum: device mode: of the band's last output row (computed on the
+// device, the step's one synchronisation); host mode: a hash of the first and last word of every row as
+// it arrived in host memory (no CPU pass over the data inside the timed region).
 int bres_step(void *h, unsigned long long *checksum, unsigned long long *launches)
 {
     ResizeBench *b = (ResizeBench *)h;
@@ -130,14 +132,12 @@ int bres_step(void *h, unsigned long long *checksum, unsigned long long *launche
                 }
                 return row;
             },
-            [&](int, CiphertextBatch &row) {
+            [&](int y, CiphertextBatch &row) {
                 if (b->host_mode) {
                     row.download(b->h_out);
                     cs = cs * 0x9E3779B97F4A7C15ull + b->h_out[0] + b->h_out[b->out_row_words - 1];
-                } else {
-                    uint64_t c = 0;
-                    check(fhe_checksum(b->ctx->handle(), row.device_data(), b->out_row_words, &c));
-                    cs = cs * 0x9E3779B97F4A7C15ull + c;
+                } else if (y == b->y1 - 1) {  // one synchronisation per step: the checksum of the last row
+                    check(fhe_checksum(b->ctx->handle(), row.device_data(), b->out_row_words, &cs));
                 }
             },
             b->y0, b->y1);
@@ -150,44 +150,50 @@ int bres_step(void *h, unsigned long long *checksum, unsigned long long *launche
         return 1;
     }
 }
-// copies of one output ciphertext and of its 16 (4) x 3 source taps for the oracle spot check:
-// output pixel (x, y) of the band, channel ch -> out (size 6 / 4), and the source rows the band holds
-// to `src` (n_src rows x ow x 3 ciphertexts, size 2) when src is not null
-int bres_spot(void *h, int x, int y, int ch, uint64_t *out, uint64_t *src, int *first_src, int *n_src)
+// Oracle spot check of one output value of the band: output pixel (x, y), channel ch -> `out` (size 6 /
+// 4); `taps`: its taps x taps source ciphertexts (size 2, row-major: tap row r, tap column c); the two
+// fractions the server encrypts for it.  Runs the engine on the single row y.
+int bres_spot(void *h, int x, int y, int ch, uint64_t *out, uint64_t *taps, double *xfrac, double *yfrac)
 {
     ResizeBench *b = (ResizeBench *)h;
     try {
-        if (first_src) *first_src = b->first_src;
-        if (n_src) *n_src = b->n_src;
-        if (src) {
-            if (b->host_mode) std::memcpy(src, b->h_src, b->row_words * b->n_src * sizeof(uint64_t));
-            else b->resident.download(src);
+        const int off = b->inter == BICUBIC ? -1 : 0, nt = b->inter == BICUBIC ? 4 : 2;
+        const float u = float(x) / float(b->dw - 1) * float(b->ow) - 0.5, v = float(y) / float(b->dh - 1) * float(b->oh) - 0.5;
+        *xfrac = u - std::floor(u);
+        *yfrac = v - std::floor(v);
+        const size_t W = b->ctx->ct_words(2);
+        std::vector<uint64_t> row_host;
+        auto source = [&](int yy, bool needed) {
+            CiphertextBatch row;
+            if (!needed || yy < b->first_src || yy >= b->first_src + b->n_src) return row;
+            if (b->host_mode) {
+                row = CiphertextBatch(*b->ctx, (size_t)b->ow * 3, 2);
+                row.upload(b->h_src + (size_t)(yy - b->first_src) * b->row_words);
+            } else {
+                row = b->resident.slice((size_t)(yy - b->first_src) * b->ow * 3, (size_t)b->ow * 3);
+            }
+            return row;
+        };
+        for (int r = 0; r < nt; ++r) {
+            const int py = std::min(std::max(int(v) + off + r, 0), b->oh - 1);
+            CiphertextBatch row = source(py, true);
+            if (!row.valid()) throw std::runtime_error("spot row outside the band");
+            for (int c = 0; c < nt; ++c) {
+                const int px = std::min(std::max(int(u) + off + c, 0), b->ow - 1);
+                check(fhe_download(b->ctx->handle(), taps + ((size_t)r * nt + c) * W, row.element((size_t)px * 3 + ch), W * sizeof(uint64_t)));
+            }
         }
-        if (out) {
-            RowResizer rr(*b->ev, *b->enc, *b->cr, b->ow, b->oh, b->dw, b->dh, b->inter);
-            rr.run(
-                [&](int yy, bool needed) {
-                    CiphertextBatch row;
-                    if (!needed || yy < b->first_src || yy >= b->first_src + b->n_src) return row;
-                    if (b->host_mode) {
-                        row = CiphertextBatch(*b->ctx, (size_t)b->ow * 3, 2);
-                        row.upload(b->h_src + (size_t)(yy - b->first_src) * b->row_words);
-                    } else {
-                        row = b->resident.slice((size_t)(yy - b->first_src) * b->ow * 3, (size_t)b->ow * 3);
-                    }
-                    return row;
-                },
-                [&](int yy, CiphertextBatch &row) {
-                    if (yy == y) row.get((size_t)x * 3 + ch).download(out);
-                },
-                y, y + 1);
-        }
+        RowResizer rr(*b->ev, *b->enc, *b->cr, b->ow, b->oh, b->dw, b->dh, b->inter);
+        rr.run(source, [&](int yy, CiphertextBatch &row) {
+            if (yy == y) row.get((size_t)x * 3 + ch).download(out);
+        }, y, y + 1);
         return 0;
     } catch (const std::exception &e) {
         g_err = e.what();
         return 1;
     }
 }
+void *bres_ctx(void *h) { return ((ResizeBench *)h)->ctx->handle(); }
 void bres_destroy(void *h)
 {
     ResizeBench *b = (ResizeBench *)h;
@@ -197,7 +203,11 @@ void bres_destroy(void *h)
     delete b;
 }
 
-void *bdec_create(int device, void *stream, uint32_t n, int npos, int degree, int order, uint32_t dbc)
+// keys: evaluation keys in coefficient form (fhe_evk_create layout) or null (no relinearisation: the
+// reference's graph); host_mode: the three inputs come from pinned host memory and all outputs go back
+// to pinned host memory inside the step
+void *bdec_create(int device, void *stream, uint32_t n, int npos, int degree, int order, uint32_t dbc, const uint64_t *keys,
+                  int host_mode, uint64_t first_ct)
 {
     try {
         auto b = std::make_unique<DecodeBench>();
@@ -205,20 +215,26 @@ void *bdec_create(int device, void *stream, uint32_t n, int npos, int degree, in
         b->ev = std::make_unique<Evaluator>(*b->ctx);
         b->enc = std::make_unique<FractionalEncoder>(*b->ctx, 100, 100);
         b->cr = std::make_unique<Encryptor>(*b->ctx);
-        b->npos = npos; b->degree = degree; b->order = order;
-        if (dbc) {
-            // timing only: any residues below every q_j serve as keys
-            const uint32_t k = b->ctx->coeff_mod_count(), digits = fhe_evk_digits(b->ctx->handle(), dbc);
-            std::vector<uint64_t> kw((size_t)k * digits * 2 * k * n);
-            uint64_t z = 0x5EED;
-            for (auto &w : kw) { z = z * 6364136223846793005ull + 1442695040888963407ull; w = z >> 12; }
-            b->evk = std::make_unique<EvaluationKeys>(*b->ctx, kw.data(), dbc, 1);
+        b->npos = npos; b->degree = degree; b->order = order; b->host_mode = host_mode != 0;
+        if (dbc && keys) {
+            b->evk = std::make_unique<EvaluationKeys>(*b->ctx, keys, dbc, 1);
             b->ev->set_relinearization(b->evk.get());
         }
         b->amplitude = Ciphertext(*b->ctx, 2); b->index = Ciphertext(*b->ctx, 2); b->count = Ciphertext(*b->ctx, 2);
-        check(fhe_fill_uniform(b->ctx->handle(), b->amplitude.device_data(), 0, 1, 2, 0xDEC));
-        check(fhe_fill_uniform(b->ctx->handle(), b->index.device_data(), 1, 1, 2, 0xDEC));
-        check(fhe_fill_uniform(b->ctx->handle(), b->count.device_data(), 2, 1, 2, 0xDEC));
+        check(fhe_fill_uniform(b->ctx->handle(), b->amplitude.device_data(), first_ct + 0, 1, 2, 0xDEC));
+        check(fhe_fill_uniform(b->ctx->handle(), b->index.device_data(), first_ct + 1, 1, 2, 0xDEC));
+        check(fhe_fill_uniform(b->ctx->handle(), b->count.device_data(), first_ct + 2, 1, 2, 0xDEC));
+        if (b->host_mode) {
+            const size_t W = b->ctx->ct_words(2);
+            void *p = nullptr;
+            check(fhe_host_alloc(3 * W * sizeof(uint64_t), &p));
+            b->h_in = (uint64_t *)p;
+            b->amplitude.download(b->h_in);
+            b->index.download(b->h_in + W);
+            b->count.download(b->h_in + 2 * W);
+            check(fhe_host_alloc((size_t)npos * b->ctx->ct_words(b->evk ? 2 : 22) * sizeof(uint64_t), &p));
+            b->h_out = (uint64_t *)p;
+        }
         b->ctx->sync();
         return b.release();
     } catch (const std::exception &e) {
@@ -232,9 +248,17 @@ int bdec_step(void *h, unsigned long long *launches, unsigned int *out_size, uin
     DecodeBench *b = (DecodeBench *)h;
     try {
         const uint64_t l0 = fhe_launch_count(b->ctx->handle());
+        const size_t W = b->ctx->ct_words(2);
+        if (b->host_mode) {
+            b->amplitude.upload(b->h_in);
+            b->index.upload(b->h_in + W);
+            b->count.upload(b->h_in + 2 * W);
+        }
         std::vector<Ciphertext> run;
         approximated_step_batched(b->amplitude, b->index, b->count, b->order, b->degree, 0.5, b->npos, 1, run, *b->ev, *b->enc, *b->cr);
         b->out_size = run.at(0).size();
+        if (b->host_mode)
+            for (size_t i = 0; i < run.size(); ++i) run[i].download(b->h_out + i * b->ctx->ct_words(b->out_size));
         if (launches) *launches = fhe_launch_count(b->ctx->handle()) - l0;
         if (out_size) *out_size = b->out_size;
         if (first_out) run[0].download(first_out);
@@ -258,6 +282,14 @@ int bdec_inputs(void *h, uint64_t *amplitude, uint64_t *index, uint64_t *count)
         return 1;
     }
 }
-void bdec_destroy(void *h) { delete (DecodeBench *)h; }
+void *bdec_ctx(void *h) { return ((DecodeBench *)h)->ctx->handle(); }
+void bdec_destroy(void *h)
+{
+    DecodeBench *b = (DecodeBench *)h;
+    if (!b) return;
+    if (b->h_in) fhe_host_free(b->h_in);
+    if (b->h_out) fhe_host_free(b->h_out);
+    delete b;
+}
 
 }  // extern "C"
