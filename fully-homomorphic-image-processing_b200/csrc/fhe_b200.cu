@@ -338,6 +338,38 @@ __global__ void k_plain_addsub(u64 *a, const u64 *scaled /*[k][n]*/, unsigned lo
     }
 }
 
+// element i of dst <- src (one ciphertext of `words` words), i < count
+__global__ void k_broadcast(u64 *dst, const u64 *__restrict__ src, unsigned long long words, unsigned long long count)
+{
+    const unsigned long long total = words * count;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        dst[i] = src[i % words];
+}
+// poly 0 of ciphertext i += Delta-scaling of its own short plaintext plains[i][0 .. ncoef) (the other
+// coefficients of the plaintext are zero); as k_plain_scale + k_plain_addsub, per element
+__global__ void k_plain_add_each(u64 *a, const u64 *__restrict__ plains, unsigned long long n_ct, uint32_t size, uint32_t ncoef, RingDev R)
+{
+    const unsigned long long total = n_ct * R.k * ncoef;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i % ncoef);
+        const uint32_t j = (uint32_t)((i / ncoef) % R.k);
+        const unsigned long long ct = i / ((unsigned long long)ncoef * R.k);
+        const u64 m = plains[ct * ncoef + c];
+        if (!m) continue;
+        u64 lo = R.delta[j] * m, hi = mulhi_u64(R.delta[j], m);
+        if (m >= R.plain_thr) {
+            u64 s = lo + R.q_mod_t;
+            hi += (s < lo);
+            lo = s;
+        }
+        const u64 q = R.limb[j].a.q;
+        u64 *p = a + (ct * size * R.k + j) * R.n + c;
+        *p = addmod(*p, barrett128(lo, hi, q, R.ratio0[j], R.ratio1[j]), q);
+    }
+}
+
 // synthetic inputs: same generator as oracle/fhe_oracle.c orc_fill_uniform
 __global__ void k_fill_uniform(u64 *dst, unsigned long long first_ct, unsigned long long total,
                                uint32_t size, u64 seed, RingDev R)

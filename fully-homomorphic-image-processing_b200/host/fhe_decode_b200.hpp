@@ -107,21 +107,63 @@ inline void approximated_step_batched(Ciphertext &amplitude, Ciphertext &index, 
     {
         Ciphertext c0(b);
         evaluator.multiply_plain(c0, encoder.encode(1.0 / ((double)order)));
-        for (size_t i = 0; i < npos; ++i) c.set(i, c0);
+        c.fill(0, npos, c0.device_data());
     }
     if (E) {
-        CiphertextBatch cos_arg(ctx, E, 2), sin_f(ctx, E, 2), cos_f(ctx, E, 2);
-        Ciphertext z;
-        for (size_t i = 0; i < npos; ++i)
-            for (int j = 1; j <= degree; ++j) {
-                const size_t e = (size_t)(j - 1) * npos + i;
-                cos_arg.set(e, offset);
-                evaluator.add_plain(offset, encoder.encode((double)i));   // :229, inside the j loop
-                encryptor.encrypt(encoder.encode(0.0), z);                // homomorphic_sin's start (:54)
-                sin_f.set(e, z);
-                encryptor.encrypt(encoder.encode(0.0), z);                // homomorphic_cos's start (:134)
-                cos_f.set(e, z);
+        // cos_arg(i, j) is the running `offset`, which receives add_plain(encode(i)) after every use
+        // (:229, inside the j loop).  add_plain adds Delta * m coefficient-wise and encode(i) has digits
+        // 0 / 1, so the offset of iteration e is the first offset plus ONE short plaintext -- the sum of
+        // the encodings added before it -- as long as no coefficient of that sum reaches the upper half
+        // of the plaintext range (then the reference's own sequence is replayed instead).
+        constexpr uint32_t NC = 32;  // an int has at most 31 binary digits
+        CiphertextBatch cos_arg(ctx, E, 2), sin_f, cos_f;
+        {
+            std::vector<uint64_t> sum(NC, 0), each(E * (size_t)NC, 0);
+            const uint64_t thr = (ctx.plain_modulus() + 1) >> 1;
+            bool closed_form = true;
+            for (size_t i = 0; i < npos && closed_form; ++i) {
+                const Plaintext pi = encoder.encode((double)i);
+                std::vector<uint32_t> digits;  // exponents of encode(i): its coefficients must all be 1
+                for (size_t cidx = 0; cidx < pi.coeffs().size(); ++cidx)
+                    if (pi.coeffs()[cidx]) {
+                        if (cidx >= NC || pi.coeffs()[cidx] != 1) closed_form = false;
+                        else digits.push_back((uint32_t)cidx);
+                    }
+                for (int j = 1; j <= degree && closed_form; ++j) {
+                    std::copy(sum.begin(), sum.end(), each.begin() + ((size_t)(j - 1) * npos + i) * NC);
+                    for (uint32_t d : digits)
+                        if (++sum[d] >= thr) closed_form = false;
+                }
             }
+            if (closed_form) {
+                cos_arg.fill(0, E, offset.device_data());
+                evaluator.add_plain_each(cos_arg, each, NC);
+            } else {
+                for (size_t i = 0; i < npos; ++i)
+                    for (int j = 1; j <= degree; ++j) {
+                        cos_arg.set((size_t)(j - 1) * npos + i, offset);
+                        evaluator.add_plain(offset, encoder.encode((double)i));
+                    }
+            }
+        }
+        // the fresh encryptions the series start from (:54, :134), in the reference's order: sin then cos
+        // per (i, j); a deterministic Encryptor yields the same ciphertext every time
+        if (encryptor.deterministic()) {
+            encryptor.encrypt(encoder.encode(0.0), sin_f, E);
+            cos_f = sin_f;
+        } else {
+            sin_f = CiphertextBatch(ctx, E, 2);
+            cos_f = CiphertextBatch(ctx, E, 2);
+            Ciphertext z;
+            for (size_t i = 0; i < npos; ++i)
+                for (int j = 1; j <= degree; ++j) {
+                    const size_t e = (size_t)(j - 1) * npos + i;
+                    encryptor.encrypt(encoder.encode(0.0), z);
+                    sin_f.set(e, z);
+                    encryptor.encrypt(encoder.encode(0.0), z);
+                    cos_f.set(e, z);
+                }
+        }
         CiphertextBatch sin_args(ctx, (size_t)degree, 2);
         for (int j = 1; j <= degree; ++j) {
             const double arg_factor = ((float)j) * M_PI / ((double)order);
@@ -134,10 +176,7 @@ inline void approximated_step_batched(Ciphertext &amplitude, Ciphertext &index, 
         {
             const CiphertextBatch sin_terms = detail::taylor_terms(sin_args, 1.0, evaluator, encoder);
             CiphertextBatch rep(ctx, E, sin_terms.size());
-            for (int j = 1; j <= degree; ++j) {
-                const Ciphertext tj = sin_terms.get((size_t)(j - 1));
-                for (size_t i = 0; i < npos; ++i) rep.set((size_t)(j - 1) * npos + i, tj);
-            }
+            for (int j = 1; j <= degree; ++j) rep.fill((size_t)(j - 1) * npos, npos, sin_terms.element((size_t)(j - 1)));
             evaluator.add_plain(sin_f, encoder.encode(-1.0));              // start + (-1), per element
             evaluator.add(rep, sin_f);                                     // + the shared terms
             sin_f = std::move(rep);

@@ -279,6 +279,12 @@ public:
         v.off_ = off_ + first * ctx_->ct_words(size_);
         return v;
     }
+    // elements [first, first + count) <- copies of the `src_size`-polynomial ciphertext at d_src (one launch)
+    void fill(size_t first, size_t count, const uint64_t *d_src)
+    {
+        if (first + count > count_) throw std::invalid_argument("batch range out of range");
+        check(fhe_device_broadcast(ctx_->handle(), element(first), d_src, size_, count));
+    }
     // element i <- c (device copy); sizes must agree
     void set(size_t i, const Ciphertext &c)
     {
@@ -357,6 +363,12 @@ public:
     {
         if (!fn_ && !ctx_) throw std::logic_error("this Encryptor holds no public key and no context");
         Ciphertext c;
+        if (deterministic() && count) {  // equal ciphertexts: one encryption, one broadcast
+            encrypt(plain, c);
+            destination = CiphertextBatch(*c.context(), count, c.size());
+            destination.fill(0, count, c.device_data());
+            return;
+        }
         for (size_t i = 0; i < count; ++i) {
             if (fn_ || i == 0) encrypt(plain, c);
             if (i == 0) destination = CiphertextBatch(*c.context(), count, c.size());
@@ -486,6 +498,14 @@ public:
     {
         require(a);
         check(fhe_sub_plain(ctx_->handle(), a.device_data(), a.count(), a.size(), table(p), 0));
+    }
+    // add_plain with a different short plaintext per element: plains[i * ncoef + c] = coefficient c of the
+    // plaintext of element i (all higher coefficients zero)
+    void add_plain_each(CiphertextBatch &a, const std::vector<uint64_t> &plains, uint32_t ncoef)
+    {
+        require(a);
+        if (plains.size() != a.count() * (size_t)ncoef) throw std::invalid_argument("one short plaintext per element expected");
+        check(fhe_add_plain_each(ctx_->handle(), a.device_data(), a.count(), a.size(), plains.data(), ncoef));
     }
     void multiply(CiphertextBatch &a, const CiphertextBatch &b)
     {

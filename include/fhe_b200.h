@@ -202,6 +202,14 @@ void fhe_form_destroy(fhe_form *form);
 int fhe_multiply_form(fhe_ctx *ctx, const fhe_form *a, uint32_t a_div, const fhe_form *b, uint32_t b_div,
                       uint64_t *dest, uint64_t n_ct);
 
+/* count copies of one ciphertext (size polynomials) into consecutive elements of d_dst */
+int fhe_device_broadcast(fhe_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, uint32_t size, uint64_t count);
+/* Evaluator::add_plain with a DIFFERENT short plaintext per ciphertext: element i of a ([n_ct][size][k][n])
+ * += plaintext i, given by its first ncoef coefficients plains[i][0 .. ncoef) (host; the rest are zero).
+ * The step approximation adds encode(i) to its running offset once per (position, j) (fhe_decode.h:229):
+ * the offsets of all positions are the first one plus short integer plaintexts, added in one launch. */
+int fhe_add_plain_each(fhe_ctx *ctx, uint64_t *a, uint64_t n_ct, uint32_t size, const uint64_t *plains, uint32_t ncoef);
+
 /* ---- resize graphs: Cubic and Linear (fhe_resize.h:143-189, :191-204) as fused device graphs --------
  * The same ciphertexts as the reference's op-by-op evaluation (every step is exact arithmetic with
  * canonical results and BEHZ multiply is a deterministic function of its operands), computed for n_ct
