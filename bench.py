@@ -157,6 +157,10 @@ def main():
                     help="dct: BASELINE config 2 (headline); resize: config 3; decode: config 5")
     ap.add_argument("--rows", type=int, default=8, help="resize: output rows per step per GPU")
     ap.add_argument("--no-side", action="store_true", help="dct: skip the short resize / decode side measurements")
+    ap.add_argument("--ingest", default="local", choices=["local", "scatter"],
+                    help="dct: also measure the one-rank ingest path (NCCL scatter of inputs from rank 0, gather of results)")
+    ap.add_argument("--ingest-blocks", type=int, default=512, help="scatter path: blocks per rank")
+    ap.add_argument("--ingest-chunk", type=int, default=128, help="scatter path: blocks per NCCL message (1 GiB at n=4096)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-tile", action="store_true", help="skip the fused RGB-tile side measurement")
     args = ap.parse_args()
@@ -290,9 +294,65 @@ def main():
                      "channel_blocks_per_s": 3 * ntiles / (tms * 1e-3), "ms": tms, "tiles": ntiles}
         jplan.close()
 
-    # ---- end to end through the C-ABI with HOST (pinned) buffers, copies inside the call -------
     del d_in, d_out
     torch.cuda.empty_cache()
+    # ---- one-rank ingest (north_star: "NCCL over NVLink only to scatter input ciphertexts and gather
+    # results"): the whole input stream is resident on rank 0, chunks travel over NCCL point-to-point,
+    # every rank computes its share, results return to rank 0's output stream (ingest.py)
+    ingest_info = None
+    if args.ingest == "scatter":
+        ingest = importlib.import_module("fully-homomorphic-image-processing_b200.ingest")
+        total, bw = world * args.ingest_blocks, ctx.block_words()
+        src = dst = None
+        if rank == 0:
+            src = torch.empty(total * bw, dtype=torch.int64, device="cuda")
+            dst = torch.empty(total * bw, dtype=torch.int64, device="cuda")
+            ctx.fill_uniform(src.data_ptr(), 0, total * 64)
+            ctx.sync()
+
+        def compute(inp, out, nb):
+            pkg.encrypted_dct_quantize(ctx, plan, inp.data_ptr(), out.data_ptr(), nb)
+
+        def run_ingest():
+            return ingest.scatter_compute_gather(dist, rank, world, total, args.ingest_chunk, bw, src, dst,
+                                                 lambda n: torch.empty(n, dtype=torch.int64, device="cuda"), compute)
+
+        run_ingest()                                     # warm-up (NCCL connections, buffers)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 3
+        i0.record(stream)
+        for _ in range(reps):
+            run_ingest()
+        i1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        tm = torch.tensor([i0.elapsed_time(i1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ok = True
+        if rank == 0:                                    # the gathered stream equals the local computation, chunk by chunk
+            scratch = torch.empty(args.ingest_chunk * bw, dtype=torch.int64, device="cuda")
+            for a in range(0, total, args.ingest_chunk):
+                nb = min(args.ingest_chunk, total - a)
+                pkg.encrypted_dct_quantize(ctx, plan, src[a * bw:].data_ptr(), scratch.data_ptr(), nb)
+                torch.cuda.synchronize()
+                ok = ok and bool(torch.equal(scratch[:nb * bw], dst[a * bw:(a + nb) * bw]))
+            del scratch
+            if not ok:
+                raise SystemExit("bench.py: the gathered output of the scatter path differs from the local computation")
+        ingest_info = {"what": "input stream resident in rank 0's HBM, chunks scattered to the ranks and results gathered back "
+                               "over NCCL point-to-point (3-stage pipeline, 2 buffers per direction per rank), blocks/s of the whole job",
+                       "value": total * reps / (float(tm.item()) * 1e-3), "unit": UNIT, "blocks": total, "blocks_per_rank": args.ingest_blocks,
+                       "chunk_blocks": args.ingest_chunk, "chunk_bytes": args.ingest_chunk * bw * 8, "ms": float(tm.item()) / reps,
+                       "bytes_over_nvlink_per_direction": (total - args.ingest_blocks) * bw * 8, "gathered_equals_local": ok}
+        del src, dst
+        torch.cuda.empty_cache()
+
+    # ---- end to end through the C-ABI with HOST (pinned) buffers, copies inside the call -------
     EB = args.e2e_blocks
     ebytes = EB * ctx.block_words() * 8
     h_in, h_out = pkg.host_alloc(ebytes), pkg.host_alloc(ebytes)
@@ -389,7 +449,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": ebytes, "d2h_bytes_per_step": ebytes,
                     "blocks_per_step": EB, "steps": e2e_steps},
             "roofline": roofline, "cpu_baseline": cpu, "server_jpeg_tile": tile_info,
-            "output_checksum_xor": hex(int(cs_t.item())), "parity_spot_check": parity, **side,
+            "output_checksum_xor": hex(int(cs_t.item())), "parity_spot_check": parity, "ingest_scatter": ingest_info, **side,
         }))
     if world > 1:
         dist.destroy_process_group()

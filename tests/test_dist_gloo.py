@@ -68,3 +68,57 @@ def test_two_rank_sharding_matches_single_rank(oracle_mod):
         o.encrypted_dct(x)
         ref ^= o.checksum(x) & 0x7FFFFFFFFFFFFFFF
     assert cnt == nblocks and cs == ref and tmax == float(world)
+
+
+def _ingest_worker(rank, world, port, total, chunk, unit, q):
+    import importlib
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    ingest = importlib.import_module(PKG_NAME + ".ingest")
+    src = torch.arange(total * unit, dtype=torch.int64) if rank == 0 else None
+    dst = torch.full((total * unit,), -1, dtype=torch.int64) if rank == 0 else None
+    seen = []
+
+    def compute(inp, out, n_units):
+        # the stand-in for the DCT: an invertible map that also records which rank handled what
+        seen.append((int(inp[0]) // unit, n_units))
+        out[:n_units * unit] = inp[:n_units * unit] * 3 + (rank + 1)
+
+    done = ingest.scatter_compute_gather(dist, rank, world, total, chunk, unit, src, dst,
+                                         lambda n: torch.empty(n, dtype=torch.int64), compute)
+    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(counts, torch.tensor([done], dtype=torch.int64))
+    if rank == 0:
+        q.put((dst.clone(), [int(c.item()) for c in counts], seen))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_one_rank_ingest_schedule_delivers_every_chunk_once_and_in_place():
+    """the NCCL scatter / compute / gather pipeline of ingest.py on gloo, world size 2 and 3: ragged
+    shares (7 units, chunks of 2), every unit computed exactly once by the rank that owns it, results
+    land at the unit's position of the ingest rank's output stream"""
+    import importlib
+    ingest = importlib.import_module(PKG_NAME + ".ingest")
+    for world in (2, 3):
+        total, chunk, unit = 7, 2, 5
+        ctx = mp.get_context("spawn")
+        q = ctx.Queue()
+        port = _free_port()
+        procs = [ctx.Process(target=_ingest_worker, args=(r, world, port, total, chunk, unit, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        dst, counts, seen0 = q.get(timeout=240)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        assert sum(counts) == total
+        want = torch.empty(total * unit, dtype=torch.int64)
+        for r in range(world):
+            lo, hi = ingest.shard_range(total, r, world)
+            assert counts[r] == hi - lo
+            want[lo * unit:hi * unit] = torch.arange(lo * unit, hi * unit) * 3 + (r + 1)
+        assert (dst == want).all()
+        lo0, hi0 = ingest.shard_range(total, 0, world)
+        assert seen0 == [(a, b - a) for a, b in ingest.chunk_ranges(lo0, hi0, chunk)]
