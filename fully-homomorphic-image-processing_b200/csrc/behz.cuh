@@ -26,7 +26,7 @@
 //
 // Data layout: a polynomial in base q is [k][n]; in base B_sk = B u {m_sk} it is [nb][n], m_sk last.
 #pragma once
-#include "ntt.cuh"
+#include "ntt_generic.cuh"
 
 namespace fhe {
 
@@ -57,8 +57,6 @@ struct BehzDev {
 };
 
 FHE_HD u64 barrett_u128(u128d z, u64 q, u64 r0, u64 r1) { return barrett128((u64)z, (u64)(z >> 64), q, r0, r1); }
-// x * c.w mod q in [0, 2q) for any x < 2^64, c = {w, floor(w 2^64 / q)} (Shoup's exact quotient)
-FHE_HD u64 mulsh(u64 x, W2 c, u64 q) { return x * c.w - mulhi_u64(x, c.p) * q; }
 // z mod p, canonical, for an auxiliary prime p = 2^55 - delta (delta < 2^26) and z < 2^119 (every
 // accumulator here is a sum of at most 33 products of two values below 2^55 and 2^55: < 2^116).
 // Three folds of the part above bit 55 (2^55 = delta mod p): 64 x 26, 36 x 26 and 8 x 26-bit products

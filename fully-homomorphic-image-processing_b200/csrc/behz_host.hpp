@@ -34,7 +34,6 @@ struct HostBehz {
     std::vector<HostLimb> limbs;  // B_sk, m_sk last: the same tables and constants as a limb of q
 };
 
-inline W2 h_shoup64(u64 w, u64 q) { return W2{w, (u64)((((u128)w) << 64) / q)}; }
 inline u64 h_prod_except(const std::vector<u64> &list, size_t skip, u64 p)
 {
     u64 r = 1 % p;

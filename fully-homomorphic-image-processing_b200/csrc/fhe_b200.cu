@@ -17,6 +17,7 @@
 #include "behz_host.hpp"
 #include "dct.cuh"
 #include "ntt.cuh"
+#include "ntt_generic.cuh"
 #include "ring_host.hpp"
 
 using namespace fhe;
@@ -71,6 +72,64 @@ __global__ void __launch_bounds__(1 << (LOGN - LOGE), NTT_MIN_CTAS(LOGN, LOGE)) 
     const LimbDev lp = R.limb[j];
     ntt_inv_pass<LOGN, LOGE, LAST, SCALE>(tau, gin, gout, smem, itw, lp);
     ntt_inv_passes<LOGN, LOGE, SCALE, LAST - 1, 0>(tau, gin, gout, smem, itw, lp);
+}
+
+// The same three kernels for a context with a prime outside the window of the lazy arithmetic
+// (ntt_generic.cuh: Harvey butterflies, any prime below 2^61): forward (canonical output), inverse,
+// multiply_plain.
+template <int LOGN, int LOGE>
+__global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_ntt_fwd_g(const u64 *in, u64 *out, RingDev R)
+{
+    using S = NttShape<LOGN, LOGE>;
+    constexpr int LAST = S::NPASS - 1;
+    extern __shared__ u64 smem[];
+    const size_t p = blockIdx.x;
+    const int j = (int)(p % R.k), tau = threadIdx.x;
+    const u64 *gin = in + p * S::N;
+    u64 *gout = out + p * S::N;
+    const W2 *tw = R.tw + (size_t)j * S::N;
+    const LimbDev lp = R.limb[j];
+    ntg_fwd_passes<LOGN, LOGE, 0, LAST>(tau, gin, gout, smem, tw, lp);
+    ntg_fwd_pass<LOGN, LOGE, LAST>(tau, gin, gout, smem, tw, lp);
+}
+template <int LOGN, int LOGE, bool SCALE>
+__global__ void __launch_bounds__(1 << (LOGN - LOGE)) k_ntt_inv_g(const u64 *in, u64 *out, RingDev R)
+{
+    using S = NttShape<LOGN, LOGE>;
+    constexpr int LAST = S::NPASS - 1;
+    extern __shared__ u64 smem[];
+    const size_t p = blockIdx.x;
+    const int j = (int)(p % R.k), tau = threadIdx.x;
+    const u64 *gin = in + p * S::N;
+    u64 *gout = out + p * S::N;
+    const W2 *itw = R.itw + (size_t)j * S::N;
+    const LimbDev lp = R.limb[j];
+    ntg_inv_pass<LOGN, LOGE, LAST, SCALE>(tau, gin, gout, smem, itw, lp);
+    ntg_inv_passes<LOGN, LOGE, SCALE, LAST - 1, 0>(tau, gin, gout, smem, itw, lp);
+}
+template <int LOGN, int LOGE>
+__global__ void __launch_bounds__(1 << (LOGN - LOGE))
+k_mulplain_g(const u64 *in, u64 *out, const W2 *__restrict__ table, RingDev R)
+{
+    using S = NttShape<LOGN, LOGE>;
+    constexpr int LAST = S::NPASS - 1;
+    extern __shared__ u64 smem[];
+    const size_t p = blockIdx.x;
+    const int j = (int)(p % R.k), tau = threadIdx.x;
+    const u64 *gin = in + p * S::N;
+    u64 *gout = out + p * S::N;
+    const W2 *tw = R.tw + (size_t)j * S::N, *itw = R.itw + (size_t)j * S::N;
+    const W2 *tab = table + (size_t)j * S::N;
+    const LimbDev lp = R.limb[j];
+    ntg_fwd_passes<LOGN, LOGE, 0, LAST>(tau, gin, gout, smem, tw, lp);
+    u64 v[S::E];
+    ntt_fwd_load<LOGN, LOGE, LAST>(v, tau, gin, smem);
+    ntg_fwd_compute<LOGN, LOGE, LAST>(v, tau, tw, lp);
+#pragma unroll
+    for (int e = 0; e < S::E; ++e) v[e] = mulsh(v[e], tab[e * S::T + tau], lp.a.q);  // [0, 2q): the inverse's input range
+    ntg_inv_compute<LOGN, LOGE, LAST, false>(v, tau, itw, lp);
+    ntt_inv_store<LOGN, LOGE, LAST>(v, tau, gout, smem);
+    ntg_inv_passes<LOGN, LOGE, false, LAST - 1, 0>(tau, gin, gout, smem, itw, lp);
 }
 
 // Evaluator::multiply_plain as ONE kernel per limb-poly: forward NTT (lazy), dyadic product with
@@ -308,7 +367,7 @@ __global__ void k_plain_scale(const u64 *plain, u64 *out, unsigned long long tot
 // w -> (w, floor(w 2^63 / q)), the mulc constant form; optional second factor (w = a*b mod q
 // first) and optional factor n^-1 (tables that feed an inverse NTT without its own scaling)
 __global__ void k_make_shoup(const u64 *a, const u64 *b, W2 *out, unsigned long long total,
-                             unsigned long long b_period, int times_ninv, RingDev R)
+                             unsigned long long b_period, int times_ninv, RingDev R, int scale_bits = 63)
 {
     for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < total;
          i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -319,7 +378,7 @@ __global__ void k_make_shoup(const u64 *a, const u64 *b, W2 *out, unsigned long 
         if (times_ninv) w = mulmod_barrett(w, R.limb[j].ninv.w, q, R.ratio0[j], R.ratio1[j]);
         W2 r;
         r.w = w;
-        r.p = (u64)((((unsigned __int128)w) << 63) / q);
+        r.p = (u64)((((unsigned __int128)w) << scale_bits) / q);  // 63: mulc; 64: mulsh (generic contexts)
         out[i] = r;
     }
 }
@@ -418,6 +477,7 @@ struct fhe_ctx {
     RingDev dev{};
     W2 *d_tw = nullptr, *d_itw = nullptr;
     int sm_count = 148;
+    bool generic = false;  // a coeff_modulus prime outside [2^40, 2^55): ntt_generic.cuh kernels, no fused DCT
     uint64_t launches = 0;
     uint32_t dct_chunk_blocks = 0;
     // staging for the host-buffer path
@@ -522,14 +582,38 @@ static int launch_fwd_mode(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, 
     return FHE_OK;
 }
 template <int LOGN, int LOGE>
+static int launch_fwd_generic(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, cudaStream_t st)
+{
+    using S = NttShape<LOGN, LOGE>;
+    const size_t smem = S::SMEM_WORDS * sizeof(u64);
+    if (int rc = set_smem(k_ntt_fwd_g<LOGN, LOGE>, smem)) return rc;
+    k_ntt_fwd_g<LOGN, LOGE><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
+    launched(c, "k_ntt_fwd_g");
+    CU_TRY(cudaGetLastError());
+    return FHE_OK;
+}
+template <int LOGN, int LOGE, bool SCALE>
+static int launch_inv_generic(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, cudaStream_t st)
+{
+    using S = NttShape<LOGN, LOGE>;
+    const size_t smem = S::SMEM_WORDS * sizeof(u64);
+    if (int rc = set_smem(k_ntt_inv_g<LOGN, LOGE, SCALE>, smem)) return rc;
+    k_ntt_inv_g<LOGN, LOGE, SCALE><<<(unsigned)npoly, S::T, smem, st>>>(in, out, c->dev);
+    launched(c, "k_ntt_inv_g");
+    CU_TRY(cudaGetLastError());
+    return FHE_OK;
+}
+template <int LOGN, int LOGE>
 static int launch_fwd(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, int mode, cudaStream_t st)
 {
+    if (c->generic) return launch_fwd_generic<LOGN, LOGE>(c, in, out, npoly, st);  // canonical in every mode
     if (mode == NTT_OUT_CANON) return launch_fwd_mode<LOGN, LOGE, NTT_OUT_CANON>(c, in, out, npoly, st);
     return launch_fwd_mode<LOGN, LOGE, NTT_OUT_REDUCED>(c, in, out, npoly, st);
 }
 template <int LOGN, int LOGE, bool SCALE>
 static int launch_inv(fhe_ctx *c, const u64 *in, u64 *out, uint64_t npoly, cudaStream_t st)
 {
+    if (c->generic) return launch_inv_generic<LOGN, LOGE, SCALE>(c, in, out, npoly, st);
     using S = NttShape<LOGN, LOGE>;
     const size_t smem = S::SMEM_WORDS * sizeof(u64);
     if (int rc = set_smem(k_ntt_inv<LOGN, LOGE, SCALE>, smem)) return rc;
@@ -543,6 +627,13 @@ static int launch_mulplain(fhe_ctx *c, const u64 *in, u64 *out, const W2 *tab, u
 {
     using S = NttShape<LOGN, LOGE>;
     const size_t smem = S::SMEM_WORDS * sizeof(u64);
+    if (c->generic) {
+        if (int rc = set_smem(k_mulplain_g<LOGN, LOGE>, smem)) return rc;
+        k_mulplain_g<LOGN, LOGE><<<(unsigned)npoly, S::T, smem, st>>>(in, out, tab, c->dev);
+        launched(c, "k_mulplain_g");
+        CU_TRY(cudaGetLastError());
+        return FHE_OK;
+    }
     if (int rc = set_smem(k_mulplain<LOGN, LOGE>, smem)) return rc;
     k_mulplain<LOGN, LOGE><<<(unsigned)npoly, S::T, smem, st>>>(in, out, tab, c->dev);
     launched(c, "k_mulplain");
@@ -615,7 +706,7 @@ int fhe_ctx_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, int de
     auto c = std::make_unique<fhe_ctx>();
     std::string err;
     if (!build_ring(c->host, n, k, q, t, err)) return fail(FHE_ERR_INVALID_ARGUMENT, err);
-    if (!c->host.unsupported.empty()) return fail(FHE_ERR_UNSUPPORTED, c->host.unsupported);
+    c->generic = c->host.generic;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -967,7 +1058,7 @@ static int build_plain_tables(fhe_ctx *c, const uint64_t *plain, uint32_t count,
         k_plain_lift<<<g, 256, 0, c->stream>>>(d_plain, d_lift, total, c->dev);
         launched(c, "k_plain_lift");
         if ((rc = ntt_forward(c, d_lift, d_lift, (uint64_t)count * k, NTT_OUT_CANON, c->stream))) break;
-        if (d_ntt) { k_make_shoup<<<g, 256, 0, c->stream>>>(d_lift, nullptr, d_ntt, total, 1, ntt_times_ninv, c->dev); launched(c, "k_make_shoup"); }
+        if (d_ntt) { k_make_shoup<<<g, 256, 0, c->stream>>>(d_lift, nullptr, d_ntt, total, 1, ntt_times_ninv, c->dev, c->generic ? 64 : 63); launched(c, "k_make_shoup"); }
         if (d_values_out && cudaMemcpyAsync(d_values_out, d_lift, total * sizeof(u64), cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) { rc = fail(FHE_ERR_CUDA, "table copy failed"); break; }
         if (cudaStreamSynchronize(c->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) { rc = fail(FHE_ERR_CUDA, "plaintext table kernels failed"); break; }
     } while (0);
@@ -1128,6 +1219,9 @@ int fhe_dct_plan_create(fhe_ctx *c, const uint64_t *dct_consts, const uint64_t *
     if (int rc = check_ctx(c)) return rc;
     if (!dct_consts || !eighth || !out) return fail(FHE_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
+    if (c->generic)
+        return fail(FHE_ERR_UNSUPPORTED, "the fused DCT needs every coeff_modulus prime in [2^40, 2^55) (SEAL 2.3's coeff_modulus_128 defaults are); "
+                                         "with this chain evaluate encrypted_dct through the Evaluator entry points");
     const uint32_t n = c->host.n, k = c->host.k;
     // Evaluator::multiply_plain throws on a zero plaintext: so does plan creation.
     auto zero = [&](const uint64_t *p) { for (uint32_t i = 0; i < n; ++i) if (p[i]) return false; return true; };

@@ -27,7 +27,7 @@ struct HostRing {
     uint32_t n = 0, logn = 0, k = 0;
     u64 t = 0, q_mod_t = 0, plain_thr = 0;
     int max_qbits = 0;
-    std::string unsupported;  // non-empty: valid SEAL parameters this build's lazy arithmetic cannot run
+    bool generic = false;     // a prime outside [2^40, 2^55): every limb runs the Harvey arithmetic of ntt_generic.cuh
     std::vector<HostLimb> limbs;
 };
 
@@ -43,6 +43,8 @@ inline u64 h_powmod(u64 b, u64 e, u64 q)
 inline u64 h_invmod(u64 a, u64 q) { return h_powmod(a, q - 2, q); }
 // multiplier constant with its mulc companion floor(w 2^63 / q)  (modarith.cuh)
 inline W2 h_shoup(u64 w, u64 q) { return W2{w, (u64)((((u128)w) << 63) / q)}; }
+// ... and with the exact Shoup companion floor(w 2^64 / q) (ntt_generic.cuh mulsh, behz.cuh)
+inline W2 h_shoup64(u64 w, u64 q) { return W2{w, (u64)((((u128)w) << 64) / q)}; }
 inline LimbArith h_limb_arith(u64 q)
 {
     LimbArith a;
@@ -98,9 +100,11 @@ inline u64 h_min_primitive_root(u64 q, uint32_t n)
     return best;
 }
 
-// NTT tables and arithmetic constants of one prime (q < 2^55 for the lazy arithmetic, 1 mod 2n)
-inline bool h_build_limb(HostLimb &L, u64 qj, uint32_t n, uint32_t logn, std::string &err)
+// NTT tables and arithmetic constants of one prime (1 mod 2n); generic: Shoup companions scaled by 2^64
+// for ntt_generic.cuh instead of mulc's 2^63 (which needs q < 2^55)
+inline bool h_build_limb(HostLimb &L, u64 qj, uint32_t n, uint32_t logn, std::string &err, bool generic = false)
 {
+    auto shoup = [generic](u64 w, u64 q) { return generic ? h_shoup64(w, q) : h_shoup(w, q); };
     L.q = qj;
     u128 ratio = (~(u128)0) / qj;  // floor(2^128/q): q odd, never divides 2^128
     L.ratio0 = (u64)ratio; L.ratio1 = (u64)(ratio >> 64);
@@ -112,8 +116,8 @@ inline bool h_build_limb(HostLimb &L, u64 qj, uint32_t n, uint32_t logn, std::st
     std::vector<W2> seal_tw(n), seal_itw(n);
     for (uint32_t idx = 0; idx < n; ++idx) {
         u64 w = pw[h_bitrev(idx, logn)];
-        seal_tw[idx] = h_shoup(w, qj);
-        seal_itw[idx] = h_shoup(h_invmod(w, qj), qj);
+        seal_tw[idx] = shoup(w, qj);
+        seal_itw[idx] = shoup(h_invmod(w, qj), qj);
     }
     L.tw.assign(n, W2{0, 0}); L.itw.assign(n, W2{0, 0});
     switch (logn) {
@@ -127,8 +131,8 @@ inline bool h_build_limb(HostLimb &L, u64 qj, uint32_t n, uint32_t logn, std::st
     u64 ninv = h_invmod(n % qj, qj);
     L.itw1 = seal_itw[1].w;
     L.dev.a = h_limb_arith(qj);
-    L.dev.ninv = h_shoup(ninv, qj);
-    L.dev.ninv_w1 = h_shoup(h_mulmod(ninv, L.itw1, qj), qj);
+    L.dev.ninv = shoup(ninv, qj);
+    L.dev.ninv_w1 = shoup(h_mulmod(ninv, L.itw1, qj), qj);
     L.dev.iw1 = seal_itw[1];
     return true;
 }
@@ -146,8 +150,7 @@ inline bool build_ring(HostRing &R, uint32_t n, uint32_t k, const uint64_t *q, u
         HostLimb &L = R.limbs[j];
         u64 qj = q[j];
         if (qj >> 61) { err = "coeff_modulus primes must be below 2^61"; return false; }
-        if (qj >> 55) { R.unsupported = "coeff_modulus primes of 55 bits or fewer are supported by this build (SEAL 2.3 coeff_modulus_128 uses 54/55-bit primes)"; }
-        if (qj >> 40 == 0) { R.unsupported = "coeff_modulus primes below 2^40 are not supported by this build"; }
+        if ((qj >> 55) || (qj >> 40) == 0) R.generic = true;  // outside the window of the lazy arithmetic
         if (qj <= t) { err = "coeff_modulus primes must exceed plain_modulus"; return false; }
         if ((qj - 1) % (2ull * n)) { err = "coeff_modulus prime is not 1 mod 2n"; return false; }
         if (!h_is_prime(qj)) { err = "coeff_modulus element is not prime"; return false; }
@@ -155,8 +158,9 @@ inline bool build_ring(HostRing &R, uint32_t n, uint32_t k, const uint64_t *q, u
             if (q[i] == qj) { err = "coeff_modulus primes must be distinct"; return false; }
         int bits = 64 - __builtin_clzll(qj);
         if (bits > R.max_qbits) R.max_qbits = bits;
-        if (!h_build_limb(L, qj, n, R.logn, err)) return false;
     }
+    for (uint32_t j = 0; j < k; ++j)
+        if (!h_build_limb(R.limbs[j], q[j], n, R.logn, err, R.generic)) return false;
     // q = prod q_j (multi-word), Delta = floor(q/t), q mod t
     std::vector<u64> big(1, 1);
     for (uint32_t j = 0; j < k; ++j) {
