@@ -149,7 +149,7 @@ inline bool build_ring(HostRing &R, uint32_t n, uint32_t k, const uint64_t *q, u
     for (uint32_t j = 0; j < k; ++j) {
         HostLimb &L = R.limbs[j];
         u64 qj = q[j];
-        if (qj >> 61) { err = "coeff_modulus primes must be below 2^61"; return false; }
+        if (qj >> 60) { err = "coeff_modulus primes must have at most 60 bits"; return false; }  // SEAL 2.3's SmallModulus limit
         if ((qj >> 55) || (qj >> 40) == 0) R.generic = true;  // outside the window of the lazy arithmetic
         if (qj <= t) { err = "coeff_modulus primes must exceed plain_modulus"; return false; }
         if ((qj - 1) % (2ull * n)) { err = "coeff_modulus prime is not 1 mod 2n"; return false; }

@@ -156,7 +156,7 @@ void *emu_ring_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, cha
 {
     auto R = std::make_unique<HostRing>();
     std::string e;
-    if (!build_ring(*R, n, k, q, t, e) || !(e = R->unsupported).empty()) {
+    if (!build_ring(*R, n, k, q, t, e) || (R->generic && !(e = "generic chain: the emulation covers the lazy kernels only").empty())) {
         if (err && errlen > 0) { std::strncpy(err, e.c_str(), errlen - 1); err[errlen - 1] = 0; }
         return nullptr;
     }

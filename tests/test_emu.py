@@ -148,7 +148,7 @@ def test_ring_rejects_bad_parameters(emu_lib):
         (4096, [0x7fffffff380003]),            # not 1 mod 2n / not prime
         (4096, [0x7fffffff380001] * 2),        # duplicate prime
         (4096, [12289]),                       # <= t
-        (4096, [0x1fffffffffe00001]),          # 61-bit prime: valid SEAL modulus, unsupported by this build
+        (4096, [0x1fffffffffe00001]),          # 61 bits: above SEAL 2.3's 60-bit limit for a coeff_modulus prime
     ]
     for n, qs in bad:
         assert not emu_lib.emu_ring_create(n, len(qs), (C.c_uint64 * len(qs))(*qs), 1 << 14, err, 256)
