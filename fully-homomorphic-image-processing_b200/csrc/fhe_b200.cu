@@ -485,6 +485,11 @@ struct fhe_ctx {
     u64 *stage[kSlots] = {nullptr, nullptr, nullptr};
     size_t stage_blocks = 0;
     cudaEvent_t ev_in[kSlots]{}, ev_comp[kSlots]{}, ev_out[kSlots]{};
+    // fhe_upload_async / fhe_download_async / fhe_transfer_fence
+    static constexpr int kDown = 8;
+    cudaEvent_t ev_mark = nullptr, ev_up = nullptr, ev_down[kDown]{};
+    bool up_pending = false;
+    uint64_t down_issued = 0, down_waited = 0;  // downloads issued / known complete
     unsigned long long *d_scratch = nullptr;
     // optional per-kernel timing of the DCT path
     bool stage_timing = false;
@@ -738,6 +743,9 @@ int fhe_ctx_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, int de
         CU_TRY(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
         CU_TRY(cudaEventCreateWithFlags(&c->ev_out[i], cudaEventDisableTiming));
     }
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_mark, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
+    for (int i = 0; i < fhe_ctx::kDown; ++i) CU_TRY(cudaEventCreateWithFlags(&c->ev_down[i], cudaEventDisableTiming));
     const size_t tbytes = (size_t)k * n * sizeof(W2);
     CU_TRY(cudaMalloc(&c->d_tw, tbytes));
     CU_TRY(cudaMalloc(&c->d_itw, tbytes));
@@ -772,6 +780,10 @@ void fhe_ctx_destroy(fhe_ctx *c)
         if (c->ev_out[i]) cudaEventDestroy(c->ev_out[i]);
     }
     clear_stage_events(c);
+    if (c->ev_mark) cudaEventDestroy(c->ev_mark);
+    if (c->ev_up) cudaEventDestroy(c->ev_up);
+    for (int i = 0; i < fhe_ctx::kDown; ++i)
+        if (c->ev_down[i]) cudaEventDestroy(c->ev_down[i]);
     for (auto &m : c->prof_marks) cudaEventDestroy(m.second);
     for (auto &kv : c->alloc_size) cudaFreeAsync(kv.first, c->stream);  // parked and still-live blocks alike
     cudaStreamSynchronize(c->stream);
@@ -947,6 +959,51 @@ int fhe_download(fhe_ctx *c, void *dst, const void *src, size_t bytes)
     CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
     return FHE_OK;
+}
+
+// Asynchronous transfers on the context's two copy streams.  A transfer starts after everything queued on
+// the context's stream at the time of the call (the destination of an upload may be a recycled block that
+// earlier kernels still read; the source of a download is produced by them) and runs beside whatever is
+// queued afterwards.  fhe_transfer_fence: the context's STREAM waits for all uploads issued so far (call
+// it before the first kernel that reads an uploaded buffer); the HOST waits until all downloads but the
+// `keep_downloads` most recent ones have landed (call it before freeing or overwriting the source of an
+// older download: the host blocks, the device keeps working on what is already queued).
+static int wait_downloads(fhe_ctx *c, uint64_t keep)
+{
+    while (c->down_waited + keep < c->down_issued) {
+        CU_TRY(cudaEventSynchronize(c->ev_down[c->down_waited % fhe_ctx::kDown]));
+        ++c->down_waited;
+    }
+    return FHE_OK;
+}
+int fhe_upload_async(fhe_ctx *c, void *d_dst, const void *h_src, size_t bytes)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!d_dst || !h_src) return fail(FHE_ERR_INVALID_ARGUMENT, "null buffer");
+    CU_TRY(cudaEventRecord(c->ev_mark, c->stream));
+    CU_TRY(cudaStreamWaitEvent(c->s_in, c->ev_mark, 0));
+    CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->s_in));
+    CU_TRY(cudaEventRecord(c->ev_up, c->s_in));
+    c->up_pending = true;
+    return FHE_OK;
+}
+int fhe_download_async(fhe_ctx *c, void *h_dst, const void *d_src, size_t bytes)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (!h_dst || !d_src) return fail(FHE_ERR_INVALID_ARGUMENT, "null buffer");
+    if (int rc = wait_downloads(c, fhe_ctx::kDown - 1)) return rc;  // the event about to be reused has completed
+    CU_TRY(cudaEventRecord(c->ev_mark, c->stream));
+    CU_TRY(cudaStreamWaitEvent(c->s_out, c->ev_mark, 0));
+    CU_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c->s_out));
+    CU_TRY(cudaEventRecord(c->ev_down[c->down_issued % fhe_ctx::kDown], c->s_out));
+    ++c->down_issued;
+    return FHE_OK;
+}
+int fhe_transfer_fence(fhe_ctx *c, uint32_t keep_downloads)
+{
+    if (int rc = check_ctx(c)) return rc;
+    if (c->up_pending) CU_TRY(cudaStreamWaitEvent(c->stream, c->ev_up, 0));
+    return wait_downloads(c, keep_downloads);
 }
 
 int fhe_device_copy(fhe_ctx *c, void *dst, const void *src, size_t bytes)

@@ -37,9 +37,12 @@ struct LimbDev {
 // kernel, table and test takes it from here.  4: four passes, 64 registers, 1024 threads per SM;
 // 5: three passes, 128 registers, 512 threads per SM.  Measured equal at n = 8192 (the fourth
 // shared-memory exchange costs what the occupancy gains: multiply_plain 0.295 vs 0.302 ms per 256
-// ciphertexts, multiply 2.41 vs 2.38, square 1.88 vs 1.82; profiles/r01_notes.md) -- 5 is kept.
+// ciphertexts, multiply 2.41 vs 2.38, square 1.88 vs 1.82; profiles/r01_notes.md).  Round 2: the fused
+// tensor + inverse kernel has a load-bound prologue and gains from the 4-pass shape's occupancy
+// (k_tensor_inv 244 -> 231 ms per resize band, bicubic +1.4 %, decode +2.3 %; profiles/r02_notes.md E):
+// n = 8192 uses 4, n = 16384 stays at 5 (a 128 KiB polynomial leaves room for one CTA either way).
 #ifndef FHE_LOGE13
-#define FHE_LOGE13 5
+#define FHE_LOGE13 4
 #endif
 #ifndef FHE_LOGE14
 #define FHE_LOGE14 5

@@ -137,17 +137,18 @@ public:
             fx = fraction(xf);
         }
         int next_src = 0;
-        for (int y = y_begin; y < y_end; ++y) {
+        auto taps_of = [&](int y, int rows[4], int &yint, double &yfr) {
             const float v = float(y) / float(dh_ - 1) * float(oh_) - 0.5;
-            const int yint = int(v);
-            const double yfr = v - std::floor(v);
-            int rows[4] = {0, 0, 0, 0};
+            yint = int(v);
+            yfr = v - std::floor(v);
             for (int r = 0; r < taps_; ++r) rows[r] = std::min(std::max(yint + off_ + r, 0), oh_ - 1);
-            // window: drop what no later row needs, load what this row needs
-            const int lowest = *std::min_element(rows, rows + taps_);
-            for (auto it = src_.begin(); it != src_.end();) it = it->first < lowest ? src_.erase(it) : std::next(it);
-            for (auto it = hor_.begin(); it != hor_.end();) it = it->first < lowest ? hor_.erase(it) : std::next(it);
-            for (int r = 0; r < taps_; ++r) {
+        };
+        // request from the source every row up to the last one output row y touches
+        auto load_for = [&](int y) {
+            int rows[4] = {0, 0, 0, 0}, yi;
+            double yf;
+            taps_of(y, rows, yi, yf);
+            for (int r = 0; r < taps_; ++r)
                 while (next_src <= rows[r]) {
                     bool needed = false;
                     for (int q = 0; q < taps_; ++q) needed |= rows[q] == next_src;
@@ -158,8 +159,26 @@ public:
                     }
                     ++next_src;
                 }
+        };
+        load_for(y_begin);
+        CiphertextBatch alive[2];  // the last two output rows: a sink may still be downloading them (fhe_download_async)
+        for (int y = y_begin; y < y_end; ++y) {
+            int rows[4] = {0, 0, 0, 0}, yint = 0;
+            double yfr = 0;
+            taps_of(y, rows, yint, yfr);
+            // window: drop what no later row needs
+            const int lowest = *std::min_element(rows, rows + taps_);
+            for (auto it = src_.begin(); it != src_.end();) it = it->first < lowest ? src_.erase(it) : std::next(it);
+            for (auto it = hor_.begin(); it != hor_.end();) it = it->first < lowest ? hor_.erase(it) : std::next(it);
+            // The rows of THIS output row were requested one iteration ago: a source that uploads
+            // asynchronously (fhe_upload_async) has had the previous row's kernels to hide the copy behind.
+            // Wait for them on the stream, then request the next output row's source rows before queueing
+            // this row's kernels.  A sink may be downloading asynchronously: the row before last is about to
+            // be released (alive[] below), so all downloads but the most recent one must have landed.
+            check(fhe_transfer_fence(ctx_.handle(), 1));
+            if (y + 1 < y_end) load_for(y + 1);
+            for (int r = 0; r < taps_; ++r)
                 if (!src_.count(rows[r])) throw std::logic_error("source row left the window (bands must be fed from their first row)");
-            }
             Fraction fy;
             if (!det) {  // the reference's order: x then y for every output pixel (fhe_resize.h:230-234)
                 CiphertextBatch xf(ctx_, (size_t)dw_, 2), yf(ctx_, (size_t)dw_, 2);
@@ -198,7 +217,9 @@ public:
                 for (int r = 0; r < taps_; ++r) tp[e * taps_ + r] = hor_.at(rows[r]).element(e);
             CiphertextBatch out = graph(tp, hor_.begin()->second.size(), fy, det ? (uint32_t)count : 3u, count);
             sink(y, out);
+            alive[y & 1] = std::move(out);
         }
+        check(fhe_transfer_fence(ctx_.handle(), 0));  // asynchronous downloads of the last rows have landed
         src_.clear();
         hor_.clear();
     }

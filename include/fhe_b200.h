@@ -202,6 +202,17 @@ void fhe_form_destroy(fhe_form *form);
 int fhe_multiply_form(fhe_ctx *ctx, const fhe_form *a, uint32_t a_div, const fhe_form *b, uint32_t b_div,
                       uint64_t *dest, uint64_t n_ct);
 
+/* Asynchronous host <-> device transfers (pinned host memory: fhe_host_alloc) on the context's copy
+ * streams, for pipelines that stream rows or chunks through the device: a transfer starts after the work
+ * queued on the context's stream at the time of the call and overlaps what is queued afterwards.
+ * fhe_transfer_fence: (uploads) the context's stream waits for every upload issued so far -- call it
+ * before the first kernel that reads an uploaded buffer; (downloads) the HOST waits until all downloads
+ * except the keep_downloads most recent ones have landed -- call it before the source of an older
+ * download is freed or overwritten, and with 0 before reading the last results on the host. */
+int fhe_upload_async(fhe_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
+int fhe_download_async(fhe_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
+int fhe_transfer_fence(fhe_ctx *ctx, uint32_t keep_downloads);
+
 /* count copies of one ciphertext (size polynomials) into consecutive elements of d_dst */
 int fhe_device_broadcast(fhe_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, uint32_t size, uint64_t count);
 /* Evaluator::add_plain with a DIFFERENT short plaintext per ciphertext: element i of a ([n_ct][size][k][n])

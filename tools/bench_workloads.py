@@ -158,7 +158,7 @@ def run_resize(args, rank, world, local_rank, torch, dist, stream, sampler_cls, 
                                       "transform_floor_pixels_per_s_whole_image": g["dw"] / (mulc_row / (MULC_PEAK * 1e9))}}
     # ---- end to end: source rows from pinned host memory, output rows back to pinned host memory, inside the step
     L.bres_destroy(h)
-    e_rows = min(rows, 2)
+    e_rows = rows
     hh = L.bres_create(local_rank, C.c_void_p(stream.cuda_stream), g["n"], g["ow"], g["oh"], g["dw"], g["dh"], 1, 1, y0, y0 + e_rows)
     if not hh:
         raise SystemExit("bench: " + L.bench_graphs_error().decode())
@@ -182,7 +182,8 @@ def run_resize(args, rank, world, local_rank, torch, dist, stream, sampler_cls, 
     src_rows_e = 2 * e_rows + 2
     e2e = {"value": e2e_value, "unit": RESIZE_UNIT, "h2d_bytes_per_step": src_rows_e * g["ow"] * 3 * ct,
            "d2h_bytes_per_step": e_rows * g["dw"] * 3 * 3 * ct, "rows_per_step": e_rows, "steps": e_steps,
-           "note": "source rows uploaded and output rows downloaded synchronously inside the step (no overlap with compute yet)"}
+           "note": "source rows come from pinned host memory (fhe_upload_async, one output row ahead) and every output row goes back "
+                   "to pinned host memory (fhe_download_async) inside the step, both beside the kernels"}
     # ---- parity: one output value of the band against the oracle's op-by-op Cubic graph
     parity, cpu = None, None
     if rank == 0 and not args.no_cpu:
