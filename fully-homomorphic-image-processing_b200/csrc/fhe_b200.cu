@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -501,11 +502,13 @@ struct fhe_ctx {
     std::unordered_map<size_t, std::vector<void *>> alloc_free;
     size_t alloc_cached = 0, alloc_cache_limit = 0;
     // pinned ring for small host -> device parameter uploads that must not synchronise the stream
-    // (fhe_encrypt_transparent): kRing slots of n words, one event per slot
-    static constexpr int kRing = 32;
-    u64 *h_ring = nullptr;
+    // (stage_params): kRing slots of kStageSlot bytes of MAPPED pinned memory, one event per slot
+    static constexpr int kRing = 64;
+    static constexpr size_t kStageSlot = 64 << 10;
+    char *h_ring = nullptr, *d_ring = nullptr;
     cudaEvent_t ev_ring[kRing]{};
-    uint64_t ring_next = 0;
+    bool ring_used[kRing]{};
+    int ring_next = 0;
     // per-kernel device time (fhe_profile_begin / fhe_profile_end): an event after every launch
     bool prof_on = false;
     std::vector<std::pair<const char *, cudaEvent_t>> prof_marks;
@@ -1146,6 +1149,52 @@ __global__ void k_encrypt_transparent(const u64 *plain, u64 *dst, unsigned long 
     }
 }
 
+// Small host -> device parameter blocks (pointer tables of the resize graphs, the plaintexts of
+// server-side encryptions, short per-element plaintexts) WITHOUT the copy engine: the block is written into
+// a slot range of mapped pinned memory and the kernel reads it from there over PCIe.  A cudaMemcpyAsync
+// would neither synchronise nor cost much by itself -- but every host-to-device copy of the process shares
+// one copy-engine queue, so a 24 KB table queued behind an 800 MB row upload of the streaming resize
+// pipeline (fhe_upload_async) held its kernel back for the whole upload (measured: end-to-end resize 2.1 k
+// pixels/s with the uploads against 3.9 k without, profiles/r02_notes.md F).
+// stage_params: copies `bytes` into free slots (waits on the host only if the ring has wrapped onto slots
+// whose consumer has not finished) and returns the device address; stage_release: call after the LAST kernel
+// that reads the block has been launched.
+struct StageRef {
+    void *dptr = nullptr;
+    int first = 0, count = 0;
+};
+static int stage_params(fhe_ctx *c, const void *src, size_t bytes, StageRef *ref)
+{
+    const size_t slot = fhe_ctx::kStageSlot;
+    if (!c->h_ring) {
+        void *h = nullptr, *d = nullptr;
+        CU_TRY(cudaHostAlloc(&h, (size_t)fhe_ctx::kRing * slot, cudaHostAllocMapped | cudaHostAllocPortable));
+        CU_TRY(cudaHostGetDevicePointer(&d, h, 0));
+        c->h_ring = (char *)h;
+        c->d_ring = (char *)d;
+        for (int i = 0; i < fhe_ctx::kRing; ++i) CU_TRY(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
+    }
+    const int need = (int)((bytes + slot - 1) / slot);
+    if (need < 1 || need > fhe_ctx::kRing / 2) return fail(FHE_ERR_INVALID_ARGUMENT, "parameter block too large for the staging ring");
+    if (c->ring_next + need > fhe_ctx::kRing) c->ring_next = 0;
+    ref->first = c->ring_next;
+    ref->count = need;
+    for (int i = ref->first; i < ref->first + need; ++i)
+        if (c->ring_used[i]) CU_TRY(cudaEventSynchronize(c->ev_ring[i]));
+    memcpy(c->h_ring + (size_t)ref->first * slot, src, bytes);
+    ref->dptr = c->d_ring + (size_t)ref->first * slot;
+    c->ring_next = ref->first + need;
+    return FHE_OK;
+}
+static int stage_release(fhe_ctx *c, const StageRef &ref)
+{
+    for (int i = ref.first; i < ref.first + ref.count; ++i) {
+        CU_TRY(cudaEventRecord(c->ev_ring[i], c->stream));
+        c->ring_used[i] = true;
+    }
+    return FHE_OK;
+}
+
 int fhe_encrypt_transparent(fhe_ctx *c, const uint64_t *plain, uint32_t count, uint64_t *d_dst)
 {
     if (int rc = check_ctx(c)) return rc;
@@ -1153,30 +1202,20 @@ int fhe_encrypt_transparent(fhe_ctx *c, const uint64_t *plain, uint32_t count, u
     const uint32_t n = c->host.n, k = c->host.k;
     for (size_t i = 0; i < (size_t)count * n; ++i)
         if (plain[i] >= c->host.t) return fail(FHE_ERR_INVALID_ARGUMENT, "plaintext coefficient is not below plain_modulus");
-    u64 *d_plain = nullptr;
-    const size_t bytes = (size_t)count * n * sizeof(u64);
-    CU_TRY(cudaMallocAsync(&d_plain, bytes, c->stream));
-    // A copy from pageable memory synchronises the stream (the host would wait for every queued
-    // kernel); the plaintexts go through a pinned ring instead, one slot each, so the call returns
-    // as soon as the work is queued and `plain` may be reused by the caller at once.
-    if (!c->h_ring) {
-        CU_TRY(cudaHostAlloc(&c->h_ring, (size_t)fhe_ctx::kRing * n * sizeof(u64), cudaHostAllocDefault));
-        for (int i = 0; i < fhe_ctx::kRing; ++i) CU_TRY(cudaEventCreateWithFlags(&c->ev_ring[i], cudaEventDisableTiming));
+    // the plaintexts are staged (no stream synchronisation, no copy-engine traffic: see stage_params), a
+    // group at a time, and the kernel reads them in place; `plain` may be reused by the caller at once
+    const size_t pbytes = (size_t)n * sizeof(u64);
+    const uint32_t group = (uint32_t)std::max<size_t>(1, ((size_t)fhe_ctx::kRing / 4 * fhe_ctx::kStageSlot) / pbytes);
+    for (uint32_t i = 0; i < count; i += group) {
+        const uint32_t m = count - i < group ? count - i : group;
+        StageRef ref;
+        if (int rc = stage_params(c, plain + (size_t)i * n, m * pbytes, &ref)) return rc;
+        const unsigned long long total = (unsigned long long)m * 2 * k * n;
+        k_encrypt_transparent<<<grid_for(total, 256, c->sm_count), 256, 0, c->stream>>>((const u64 *)ref.dptr, (u64 *)d_dst + (size_t)i * 2 * k * n, total, c->dev);
+        launched(c, "k_encrypt_transparent");
+        CU_TRY(cudaGetLastError());
+        if (int rc = stage_release(c, ref)) return rc;
     }
-    for (uint32_t i = 0; i < count; ++i) {
-        const int slot = (int)(c->ring_next % fhe_ctx::kRing);
-        if (c->ring_next >= (uint64_t)fhe_ctx::kRing) CU_TRY(cudaEventSynchronize(c->ev_ring[slot]));
-        ++c->ring_next;
-        u64 *h = c->h_ring + (size_t)slot * n;
-        memcpy(h, plain + (size_t)i * n, (size_t)n * sizeof(u64));
-        CU_TRY(cudaMemcpyAsync(d_plain + (size_t)i * n, h, (size_t)n * sizeof(u64), cudaMemcpyHostToDevice, c->stream));
-        CU_TRY(cudaEventRecord(c->ev_ring[slot], c->stream));
-    }
-    const unsigned long long total = (unsigned long long)count * 2 * k * n;
-    k_encrypt_transparent<<<grid_for(total, 256, c->sm_count), 256, 0, c->stream>>>(d_plain, (u64 *)d_dst, total, c->dev);
-    launched(c, "k_encrypt_transparent");
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaFreeAsync(d_plain, c->stream));
     return FHE_OK;
 }
 

@@ -13,10 +13,13 @@
 // decode: one run-length pair through approximated_step_batched (positions x degree Taylor series),
 //   optionally with every product relinearised (synthetic evaluation keys: timing only).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
 #include <vector>
+
+#include <cuda_runtime_api.h>
 
 #include "../fully-homomorphic-image-processing_b200/host/fhe_decode_b200.hpp"
 #include "../fully-homomorphic-image-processing_b200/host/fhe_resize_b200.hpp"
@@ -33,12 +36,13 @@ struct ResizeBench {
     std::unique_ptr<Encryptor> cr;
     int ow, oh, dw, dh, inter;
     bool host_mode;
-    int y0 = 0, y1 = 0, first_src = 0, n_src = 0;
+    int y0 = 0, y1 = 0, first_src = 0, n_src = 0, n_host = 0;
     CiphertextBatch resident;         // device mode: source rows first_src .. first_src + n_src - 1
     uint64_t *h_src = nullptr;        // host mode: the same rows, pinned
     uint64_t *h_out = nullptr;        // host mode: two output rows, pinned (double buffer of the asynchronous downloads)
     size_t row_words = 0, out_row_words = 0;
     uint64_t last_checksum = 0;
+    cudaStream_t stream = nullptr;    // the stream the context works on (BRES_TRACE)
 };
 
 struct DecodeBench {
@@ -75,11 +79,15 @@ extern "C" {
 
 const char *bench_graphs_error(void) { return g_err.c_str(); }
 
-void *bres_create(int device, void *stream, uint32_t n, int ow, int oh, int dw, int dh, int inter, int host_mode, int y0, int y1)
+// host_rows (host mode): pinned source rows to hold, 0 = every row the band touches; with fewer, source row y
+// is read from slot (y - first) % host_rows -- the data is synthetic, so a long band (whose fill and drain
+// are amortised as they are over a whole image) need not pin tens of GB; the spot check reads the same slots
+void *bres_create(int device, void *stream, uint32_t n, int ow, int oh, int dw, int dh, int inter, int host_mode, int y0, int y1, int host_rows)
 {
     try {
         auto b = std::make_unique<ResizeBench>();
         b->ctx = std::make_unique<Context>(n, 1 << 14, std::vector<uint64_t>{}, device, stream);
+        b->stream = (cudaStream_t)stream;
         b->ev = std::make_unique<Evaluator>(*b->ctx);
         b->enc = std::make_unique<FractionalEncoder>(*b->ctx, 100, 100);
         b->cr = std::make_unique<Encryptor>(*b->ctx);
@@ -88,14 +96,15 @@ void *bres_create(int device, void *stream, uint32_t n, int ow, int oh, int dw, 
         int last = 0;
         band_rows(oh, dh, inter, y0, y1, b->first_src, last);
         b->n_src = last - b->first_src + 1;
+        b->n_host = host_mode && host_rows > 0 && host_rows < b->n_src ? host_rows : b->n_src;
         b->row_words = b->ctx->ct_words(2) * (size_t)ow * 3;
         b->out_row_words = b->ctx->ct_words(inter == BICUBIC ? 6 : 4) * (size_t)dw * 3;
         // the band's source rows: ciphertext index = (row * ow + x) * 3 + channel of the whole image
-        b->resident = CiphertextBatch(*b->ctx, (size_t)b->n_src * ow * 3, 2);
-        check(fhe_fill_uniform(b->ctx->handle(), b->resident.device_data(), (uint64_t)b->first_src * ow * 3, (uint64_t)b->n_src * ow * 3, 2, 0xC0F3));
+        b->resident = CiphertextBatch(*b->ctx, (size_t)b->n_host * ow * 3, 2);
+        check(fhe_fill_uniform(b->ctx->handle(), b->resident.device_data(), (uint64_t)b->first_src * ow * 3, (uint64_t)b->n_host * ow * 3, 2, 0xC0F3));
         if (b->host_mode) {
             void *p = nullptr;
-            check(fhe_host_alloc(b->row_words * b->n_src * sizeof(uint64_t), &p));
+            check(fhe_host_alloc(b->row_words * b->n_host * sizeof(uint64_t), &p));
             b->h_src = (uint64_t *)p;
             check(fhe_host_alloc(2 * b->out_row_words * sizeof(uint64_t), &p));
             b->h_out = (uint64_t *)p;
@@ -119,14 +128,28 @@ int bres_step(void *h, unsigned long long *checksum, unsigned long long *launche
     try {
         const uint64_t l0 = fhe_launch_count(b->ctx->handle());
         uint64_t cs = 0;
+        // BRES_TRACE=1 (diagnostic, stderr): per output row, how long the stream waited for the row's
+        // uploads after the previous row's kernels ("stall") and how long its own kernels ran ("busy").
+        // The engine requests row y + 1's sources right before it queues row y's kernels, after making the
+        // stream wait for row y's uploads: an event recorded then fires when row y can start.
+        const bool trace = std::getenv("BRES_TRACE") != nullptr && b->stream;
+        std::vector<cudaEvent_t> t_start, t_end;  // t_start[k]: the last mark recorded while k rows had been emitted
+        auto mark = [&](cudaEvent_t &e) {
+            if (!e) cudaEventCreate(&e);
+            cudaEventRecord(e, b->stream);
+        };
         RowResizer rr(*b->ev, *b->enc, *b->cr, b->ow, b->oh, b->dw, b->dh, b->inter);
         rr.run(
             [&](int y, bool needed) {
+                if (trace) {  // all marks of one batch of requests fire together: keep the last one per emitted-row count
+                    if (t_start.size() <= t_end.size()) t_start.resize(t_end.size() + 1, nullptr);
+                    mark(t_start[t_end.size()]);
+                }
                 CiphertextBatch row;
                 if (!needed || y < b->first_src || y >= b->first_src + b->n_src) return row;
                 if (b->host_mode) {  // pinned host -> device on the copy stream, behind the previous row's kernels
                     row = CiphertextBatch(*b->ctx, (size_t)b->ow * 3, 2);
-                    check(fhe_upload_async(b->ctx->handle(), row.device_data(), b->h_src + (size_t)(y - b->first_src) * b->row_words,
+                    check(fhe_upload_async(b->ctx->handle(), row.device_data(), b->h_src + (size_t)((y - b->first_src) % b->n_host) * b->row_words,
                                            b->row_words * sizeof(uint64_t)));
                 } else {
                     row = b->resident.slice((size_t)(y - b->first_src) * b->ow * 3, (size_t)b->ow * 3);
@@ -134,6 +157,10 @@ int bres_step(void *h, unsigned long long *checksum, unsigned long long *launche
                 return row;
             },
             [&](int y, CiphertextBatch &row) {
+                if (trace) {
+                    t_end.push_back(nullptr);
+                    mark(t_end.back());
+                }
                 if (b->host_mode) {  // device -> pinned host on the other copy stream, beside the next row's kernels
                     check(fhe_download_async(b->ctx->handle(), b->h_out + (size_t)(y & 1) * b->out_row_words, row.device_data(),
                                              b->out_row_words * sizeof(uint64_t)));
@@ -144,6 +171,17 @@ int bres_step(void *h, unsigned long long *checksum, unsigned long long *launche
             b->y0, b->y1);
         if (b->host_mode)  // run() returned after the last download landed: hash the two rows still in the buffers
             for (int s2 = 0; s2 < 2; ++s2) cs = cs * 0x9E3779B97F4A7C15ull + b->h_out[(size_t)s2 * b->out_row_words] + b->h_out[(size_t)(s2 + 1) * b->out_row_words - 1];
+        if (trace) {
+            cudaStreamSynchronize(b->stream);
+            for (size_t i = 0; i < t_end.size(); ++i) {
+                float busy = 0, stall = 0;
+                if (i < t_start.size() && t_start[i]) cudaEventElapsedTime(&busy, t_start[i], t_end[i]);
+                if (i >= 1 && i < t_start.size() && t_start[i]) cudaEventElapsedTime(&stall, t_end[i - 1], t_start[i]);
+                std::fprintf(stderr, "[bres trace %s] row %d: stall %.1f ms, busy %.1f ms\n", b->host_mode ? "host" : "device", b->y0 + (int)i, stall, busy);
+            }
+            for (auto e : t_start) if (e) cudaEventDestroy(e);
+            for (auto e : t_end) cudaEventDestroy(e);
+        }
         b->last_checksum = cs;
         if (checksum) *checksum = cs;
         if (launches) *launches = fhe_launch_count(b->ctx->handle()) - l0;
@@ -171,7 +209,7 @@ int bres_spot(void *h, int x, int y, int ch, uint64_t *out, uint64_t *taps, doub
             if (!needed || yy < b->first_src || yy >= b->first_src + b->n_src) return row;
             if (b->host_mode) {
                 row = CiphertextBatch(*b->ctx, (size_t)b->ow * 3, 2);
-                row.upload(b->h_src + (size_t)(yy - b->first_src) * b->row_words);
+                row.upload(b->h_src + (size_t)((yy - b->first_src) % b->n_host) * b->row_words);
             } else {
                 row = b->resident.slice((size_t)(yy - b->first_src) * b->ow * 3, (size_t)b->ow * 3);
             }

@@ -37,7 +37,7 @@ def shim():
     vp, u64p = C.c_void_p, C.POINTER(C.c_uint64)
     L.bench_graphs_error.restype = C.c_char_p
     L.bres_create.restype = vp
-    L.bres_create.argtypes = [C.c_int, vp, C.c_uint32] + [C.c_int] * 8
+    L.bres_create.argtypes = [C.c_int, vp, C.c_uint32] + [C.c_int] * 9
     L.bres_step.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     L.bres_spot.argtypes = [vp, C.c_int, C.c_int, C.c_int, u64p, u64p, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.bres_ctx.restype = vp
@@ -114,7 +114,7 @@ def run_resize(args, rank, world, local_rank, torch, dist, stream, sampler_cls, 
     rows = 2 if short else args.rows
     steps, warmup = (2, 1) if short else (args.steps, max(args.warmup, 3))
     y0 = 96 + rank * rows                      # a band away from the clamped borders; each rank its own (weak scaling)
-    h = L.bres_create(local_rank, C.c_void_p(stream.cuda_stream), g["n"], g["ow"], g["oh"], g["dw"], g["dh"], 1, 0, y0, y0 + rows)
+    h = L.bres_create(local_rank, C.c_void_p(stream.cuda_stream), g["n"], g["ow"], g["oh"], g["dw"], g["dh"], 1, 0, y0, y0 + rows, 0)
     if not h:
         raise SystemExit("bench: " + L.bench_graphs_error().decode())
     cs, launches = C.c_ulonglong(0), C.c_ulonglong(0)
@@ -158,8 +158,13 @@ def run_resize(args, rank, world, local_rank, torch, dist, stream, sampler_cls, 
                                       "transform_floor_pixels_per_s_whole_image": g["dw"] / (mulc_row / (MULC_PEAK * 1e9))}}
     # ---- end to end: source rows from pinned host memory, output rows back to pinned host memory, inside the step
     L.bres_destroy(h)
-    e_rows = rows
-    hh = L.bres_create(local_rank, C.c_void_p(stream.cuda_stream), g["n"], g["ow"], g["oh"], g["dw"], g["dh"], 1, 1, y0, y0 + e_rows)
+    # A band's first source rows cannot be hidden behind kernels and neither can its last download; over the
+    # whole image (192 output rows in config 3) that fill and drain are ~1 % -- over an 8-row band they were
+    # 16 % (profiles/r02_notes.md F).  So the end-to-end leg runs ONE band three times as long as the
+    # device-resident step's, its source rows cycling through the pinned rows of an 8-row band.
+    e_rows = rows if short else 3 * rows
+    hh = L.bres_create(local_rank, C.c_void_p(stream.cuda_stream), g["n"], g["ow"], g["oh"], g["dw"], g["dh"], 1, 1, y0, y0 + e_rows,
+                       2 * rows + 2)
     if not hh:
         raise SystemExit("bench: " + L.bench_graphs_error().decode())
     ecs = C.c_ulonglong(0)
@@ -171,7 +176,7 @@ def run_resize(args, rank, world, local_rank, torch, dist, stream, sampler_cls, 
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    e_steps = 1 if short else 2
+    e_steps = 1
     for _ in range(e_steps):
         estep()
     torch.cuda.synchronize()
