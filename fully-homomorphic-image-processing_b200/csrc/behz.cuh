@@ -38,6 +38,7 @@ typedef unsigned __int128 u128d;
 struct BehzDev {
     uint32_t n, logn, k, kb, nb;
     u64 q[BEHZ_MAXK], qr0[BEHZ_MAXK], qr1[BEHZ_MAXK];       // primes of q and floor(2^128 / q_i)
+    u32 qdelta[BEHZ_MAXK];                // 2^55 - q_i when that is in (0, 2^26) (fold_delta_of), else 0: Barrett
     u64 b[BEHZ_MAXB], br0[BEHZ_MAXB], br1[BEHZ_MAXB];       // B_sk
     u32 bdelta[BEHZ_MAXB];                // 2^55 - b_j (< 2^26): the auxiliary primes are 2^55 - delta
     // extension q -> B_sk (fastbconv_mtilde + mont_rq)
@@ -71,6 +72,19 @@ FHE_HD u64 fold_aux(u128d z, u64 p, u32 delta)
     const u64 s = wl + wh * delta;                                       // < 2^55 + 2^62
     const u64 r = (s & M55) + (s >> 55) * delta;                         // < 2^55 + 2^34 < 2p
     return csub(r, p);
+}
+// The primes of q themselves usually have that shape: all eight of SEAL's 55-bit defaults are
+// 2^55 - a 2^18 + 1 with 2^55 - q < 2^26 (csrc/fhe_b200.cu default chain).  fold_delta_of(q) is that
+// delta or 0 ("use Barrett"); reduce_u128 picks the route -- a uniform branch, the prime is per launch or
+// per CTA.  Both routes give the canonical residue, so which one runs is unobservable.
+FHE_HD u32 fold_delta_of(u64 q)
+{
+    const u64 top = 1ull << 55;
+    return (q < top && top - q < (1ull << 26)) ? (u32)(top - q) : 0u;
+}
+FHE_HD u64 reduce_u128(u128d z, u64 q, u64 r0, u64 r1, u32 delta)
+{
+    return delta ? fold_aux(z, q, delta) : barrett_u128(z, q, r0, r1);
 }
 // x * c mod q, canonical, c a Shoup pair scaled by 2^64
 FHE_HD u64 mulsh_canon(u64 x, W2 c, u64 q) { return csub(mulsh(x, c, q), q); }
@@ -155,7 +169,7 @@ FHE_HD void behz_scale_coeff_t(const BehzDev &B, const u64 *xq, size_t qs, const
 #pragma unroll
             for (int l = 0; l < MB; ++l)
                 if (l < kb) a2 += (u128d)z[l] * B.I[i][l];
-            out[i * os] = barrett_u128(a2, B.q[i], B.qr0[i], B.qr1[i]);
+            out[i * os] = reduce_u128(a2, B.q[i], B.qr0[i], B.qr1[i], B.qdelta[i]);
         }
 }
 // run-time sizes (tests/emu, unusual bases)
@@ -169,16 +183,17 @@ FHE_HD void behz_scale_coeff(const BehzDev &B, const u64 *xq, size_t qs, const u
 }
 
 // one (limb, position) of the tensor product: d[l] = sum_{x+y=l} a[x] b[y] mod q, operands `stride`
-// words apart per poly, 128-bit accumulation (min(s1, s2) <= 32 terms of < 2^122), one Barrett reduction
+// words apart per poly, 128-bit accumulation (min(s1, s2) <= 32 terms of < 2^122), one reduction
+// (delta: fold_delta_of(q), or 0 for Barrett)
 FHE_HD void behz_tensor_elem(const u64 *a, const u64 *b, u64 *d, size_t stride, uint32_t s1, uint32_t s2,
-                             u64 q, u64 r0, u64 r1)
+                             u64 q, u64 r0, u64 r1, u32 delta = 0)
 {
     const uint32_t sd = s1 + s2 - 1;
     for (uint32_t l = 0; l < sd; ++l) {
         u128d acc = 0;
         const uint32_t xlo = l >= s2 ? l - (s2 - 1) : 0, xhi = l < s1 ? l : s1 - 1;
         for (uint32_t x = xlo; x <= xhi; ++x) acc += (u128d)a[x * stride] * b[(l - x) * stride];
-        d[l * stride] = barrett_u128(acc, q, r0, r1);
+        d[l * stride] = reduce_u128(acc, q, r0, r1, delta);
     }
 }
 

@@ -73,6 +73,7 @@ inline bool build_behz(const HostRing &R, HostBehz &H, std::string &err)
     for (uint32_t i = 0; i < k; ++i) {
         D.q[i] = q[i];
         D.qr0[i] = R.limbs[i].ratio0; D.qr1[i] = R.limbs[i].ratio1;
+        D.qdelta[i] = fold_delta_of(q[i]);
         const u64 qhat_inv = h_invmod(h_prod_except(q, i, q[i]), q[i]);
         D.mt_qhat_inv[i] = h_shoup64(h_mulmod(qhat_inv, MT % q[i], q[i]), q[i]);
         D.qhat_mod_mt[i] = (u32)h_prod_except(q, i, MT);

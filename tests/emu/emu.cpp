@@ -134,10 +134,10 @@ int emu_multiply(void *ring, void *h, const uint64_t *a1, uint32_t s1, const uin
     prep(a2, s2, q2, b2);
     for (uint32_t i = 0; i < k; ++i)
         for (uint32_t c = 0; c < n; ++c)
-            behz_tensor_elem(q1.data() + (size_t)i * n + c, q2.data() + (size_t)i * n + c, dq.data() + (size_t)i * n + c, pq, s1, s2, B.q[i], B.qr0[i], B.qr1[i]);
+            behz_tensor_elem(q1.data() + (size_t)i * n + c, q2.data() + (size_t)i * n + c, dq.data() + (size_t)i * n + c, pq, s1, s2, B.q[i], B.qr0[i], B.qr1[i], B.qdelta[i]);
     for (uint32_t j = 0; j < nb; ++j)
         for (uint32_t c = 0; c < n; ++c)
-            behz_tensor_elem(b1.data() + (size_t)j * n + c, b2.data() + (size_t)j * n + c, db.data() + (size_t)j * n + c, pb, s1, s2, B.b[j], B.br0[j], B.br1[j]);
+            behz_tensor_elem(b1.data() + (size_t)j * n + c, b2.data() + (size_t)j * n + c, db.data() + (size_t)j * n + c, pb, s1, s2, B.b[j], B.br0[j], B.br1[j], B.bdelta[j]);
     for (uint32_t p = 0; p < sd; ++p) {
         for (uint32_t i = 0; i < k; ++i) inv_dispatch(R, i, dq.data() + p * pq + (size_t)i * n, dq.data() + p * pq + (size_t)i * n, true);
         for (uint32_t j = 0; j < nb; ++j) inv_w_dispatch(H, j, db.data() + p * pb + (size_t)j * n, db.data() + p * pb + (size_t)j * n);
