@@ -4,6 +4,7 @@ in-process through tools/libbench_graphs.so, timed with CUDA events on the strea
 on; the oracle (oracle/, CPU) only as the parity checker and as the timed CPU baseline."""
 import ctypes as C
 import importlib
+import json
 import math
 import os
 import subprocess
@@ -91,6 +92,17 @@ def _profile(pkg, ctx_handle, fn):
     return {k: {"ms": round(v[0], 4), "launches": v[1]} for k, v in prof.items() if k}
 
 
+def _traffic(workload, kernel, launches):
+    """measured DRAM bytes of one step's launches of `kernel`: ncu per-launch mean (profiles/traffic.json, captured on
+    the default geometry) x the launches the profiler counted in this step; None when there is no capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            per = json.load(f)[workload]["dram_bytes_per_launch"].get(kernel)
+        return per * launches if per else None
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def _ntt_mulc(n):
     return (n // 2) * (n.bit_length() - 1)
 
@@ -147,7 +159,8 @@ def run_resize(args, rank, world, local_rank, torch, dist, stream, sampler_cls, 
     achieved = kernel_bytes.get(dom, 0) / (prof[dom]["ms"] * 1e-3) / 1e9 if prof[dom]["ms"] else 0.0
     path_bytes_per_pixel = 3 * 3.5 * (1 << 20)   # 3.5 MiB per channel-pixel with ideal input reuse
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak[0], "unit": "GB/s",
-                "frac": achieved / peak[0], "traffic": None, "peak_source": peak[1],
+                "frac": achieved / peak[0], "traffic": _traffic("resize", dom, prof[dom]["launches"]) if rows == 8 else None,
+                "peak_source": peak[1],
                 "algorithmic_bytes_per_step": kernel_bytes.get(dom), "kernel_ms_per_step": prof,
                 "path_achieved": value / world * path_bytes_per_pixel / 1e9,
                 "path_frac": value / world * path_bytes_per_pixel / 1e9 / peak[0],
@@ -302,7 +315,8 @@ def run_decode(args, rank, world, local_rank, torch, dist, stream, sampler_cls, 
     achieved = kernel_bytes.get(dom, 0) / (prof[dom]["ms"] * 1e-3) / 1e9 if prof[dom]["ms"] else 0.0
     path_bytes = (3 + g["npos"]) * ct          # 3 ciphertexts in, npos size-2 ciphertexts out
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak[0], "unit": "GB/s", "frac": achieved / peak[0],
-                "traffic": None, "peak_source": peak[1], "algorithmic_bytes_per_step": kernel_bytes.get(dom),
+                "traffic": _traffic("decode", dom, prof[dom]["launches"]), "peak_source": peak[1],
+                "algorithmic_bytes_per_step": kernel_bytes.get(dom),
                 "kernel_ms_per_step": prof, "path_achieved": value / world * path_bytes / 1e9,
                 "path_frac": value / world * path_bytes / 1e9 / peak[0],
                 "note": "the path's algorithmic HBM bytes are tiny (3 ciphertexts in, 64 out for 10^4 ciphertext products): "
