@@ -44,9 +44,11 @@ class FheError(RuntimeError):
 
 def build(force: bool = False) -> str:
     """Compile csrc/ for sm_100a into the in-tree libfhe_b200.so (nvcc cross-compiles without a GPU)."""
+    if os.environ.get("FHE_B200_LIB"):   # an A/B build supplied by the caller: never rebuilt from here
+        return LIB_PATH
     src = os.path.join(_HERE, "csrc", "fhe_b200.cu")
     deps = [src] + [os.path.join(_HERE, "csrc", f) for f in (
-        "ntt.cuh", "dct.cuh", "modarith.cuh", "ring_host.hpp", "behz.cuh", "behz_host.hpp", "behz_api.inc",
+        "ntt.cuh", "ntt_generic.cuh", "dct.cuh", "modarith.cuh", "ring_host.hpp", "behz.cuh", "behz_host.hpp", "behz_api.inc",
         "resize_api.inc", "jpeg_api.inc")]
     deps.append(os.path.join(ROOT, "include", "fhe_b200.h"))
     stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(d) > os.path.getmtime(LIB_PATH) for d in deps)
