@@ -12,8 +12,8 @@ resident chunk of synthetic ciphertext blocks of BASELINE config 2 (server_jpeg 
 1024x1024 RGB = 49152 blocks, n=4096, k=2, t=2^14).  The 384 GiB image does not fit in HBM, so it
 is streamed as chunks of --blocks blocks (default 8192 = 1/6 of the image, 64 GiB in + 64 GiB
 out); inputs are generated on the device (seeded SplitMix64, uniform residues)
-before the timed region.  The default line also carries short side measurements of the other two
-workloads (keys "config3_resize", "config5_decode"; --no-side skips them).
+before the timed region.  The default line also carries the other two workloads at their full
+configurations with fewer steps (keys "config3_resize", "config5_decode"; --no-side skips them).
 resize.  A step is a band of --rows output rows of BASELINE config 3 (server_resize --bicubic,
 512x512 -> 256x256 RGB, n=8192, k=4) through the row engine of host/fhe_resize_b200.hpp.
 decode.  A step is one run-length pair of BASELINE config 5 (approximated_step, 64 positions, degree
@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--workload", default="dct", choices=["dct", "resize", "decode"],
                     help="dct: BASELINE config 2 (headline); resize: config 3; decode: config 5")
     ap.add_argument("--rows", type=int, default=8, help="resize: output rows per step per GPU")
-    ap.add_argument("--no-side", action="store_true", help="dct: skip the short resize / decode side measurements")
+    ap.add_argument("--no-side", action="store_true", help="dct: skip the resize / decode side measurements")
     ap.add_argument("--ingest", default="local", choices=["local", "scatter"],
                     help="dct: also measure the one-rank ingest path (NCCL scatter of inputs from rank 0, gather of results)")
     ap.add_argument("--ingest-blocks", type=int, default=512, help="scatter path: blocks per rank")
@@ -422,8 +422,8 @@ def main():
                          f"(oracle, op-by-op reference graph); single thread: {v1:.2f} blocks/s",
                "single_thread_value": v1}
 
-    # ---- short side measurements of the other two hot-path configurations (their own full lines:
-    # --workload resize / decode); every rank runs them, like the headline
+    # ---- the other two hot-path configurations, full size, fewer steps (their own lines: --workload resize /
+    # decode); every rank runs them, like the headline
     side = {}
     plan.close()
     ctx.close()
@@ -432,7 +432,7 @@ def main():
         import bench_workloads
         for key, fn in (("config3_resize", bench_workloads.run_resize), ("config5_decode", bench_workloads.run_decode)):
             try:
-                side[key] = fn(args, rank, world, local_rank, torch, dist, stream, ClockSampler, measured_peaks(), short=True)
+                side[key] = fn(args, rank, world, local_rank, torch, dist, stream, ClockSampler, measured_peaks(), side=True)
             except SystemExit as e:
                 side[key] = {"error": str(e)}
 

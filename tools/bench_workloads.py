@@ -139,12 +139,13 @@ def resize_band_work(rows, dw, k, n, first_src_rows):
     return hor, ver, ntts * _ntt_mulc(n)
 
 
-def run_resize(args, rank, world, local_rank, torch, dist, stream, sampler_cls, peak, short=False):
+def run_resize(args, rank, world, local_rank, torch, dist, stream, sampler_cls, peak, side=False):
     pkg = importlib.import_module(PKG)
     L = shim()
     g = RESIZE
-    rows = 2 if short else args.rows
-    steps, warmup = (2, 1) if short else (args.steps, max(args.warmup, 3))
+    # side=True: the run bench.py's default line carries under "config3_resize" -- the SAME configuration, fewer steps
+    rows = args.rows
+    steps, warmup = (2, 3) if side else (args.steps, max(args.warmup, 3))
     y0 = 96 + rank * rows                      # a band away from the clamped borders; each rank its own (weak scaling)
     h = L.bres_create(local_rank, C.c_void_p(stream.cuda_stream), g["n"], g["ow"], g["oh"], g["dw"], g["dh"], 1, 0, y0, y0 + rows, 0)
     if not h:
@@ -195,7 +196,7 @@ def run_resize(args, rank, world, local_rank, torch, dist, stream, sampler_cls, 
     # whole image (192 output rows in config 3) that fill and drain are ~1 % -- over an 8-row band they were
     # 16 % (profiles/r02_notes.md F).  So the end-to-end leg runs ONE band three times as long as the
     # device-resident step's, its source rows cycling through the pinned rows of an 8-row band.
-    e_rows = rows if short else 3 * rows
+    e_rows = 3 * rows
     hh = L.bres_create(local_rank, C.c_void_p(stream.cuda_stream), g["n"], g["ow"], g["oh"], g["dw"], g["dh"], 1, 1, y0, y0 + e_rows,
                        2 * rows + 2)
     if not hh:
@@ -280,14 +281,12 @@ def decode_keys(n, k, nd, seed=0x5EED):
     return rng.integers(0, 1 << 50, size=k * nd * 2 * k * n, dtype=np.uint64)
 
 
-def run_decode(args, rank, world, local_rank, torch, dist, stream, sampler_cls, peak, short=False):
+def run_decode(args, rank, world, local_rank, torch, dist, stream, sampler_cls, peak, side=False):
     import numpy as np
     pkg = importlib.import_module(PKG)
     L = shim()
     g = dict(DECODE)
-    if short:
-        g["npos"], g["degree"] = 16, 4
-    steps, warmup = (2, 1) if short else (args.steps, max(args.warmup, 3))
+    steps, warmup = (3, 3) if side else (args.steps, max(args.warmup, 3))   # side: same configuration, fewer steps
     k, nd = 4, 2
     keys = decode_keys(g["n"], k, nd)
     u64p = C.POINTER(C.c_uint64)
@@ -358,7 +357,7 @@ def run_decode(args, rank, world, local_rank, torch, dist, stream, sampler_cls, 
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    e_steps = 1 if short else max(2, min(steps, 4))
+    e_steps = max(2, min(steps, 4))
     for _ in range(e_steps):
         estep()
     torch.cuda.synchronize()
@@ -394,7 +393,7 @@ def run_decode(args, rank, world, local_rank, torch, dist, stream, sampler_cls, 
     return {
         "metric": DECODE_METRIC, "value": value, "unit": DECODE_UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-        "config": {"workload": DECODE_WORKLOAD if not short else DECODE_WORKLOAD.replace("64 positions, degree 12", f"{g['npos']} positions, degree {g['degree']} (short side run)"),
+        "config": {"workload": DECODE_WORKLOAD,
                    "positions": g["npos"], "degree": g["degree"], "order": g["order"], "dbc": g["dbc"], "out_ct_size": int(osz.value),
                    "l2": "working set of a step (GiB) larger than L2", "parallelism": f"run-length pairs x{world}"},
         "clocks": clocks, "gpu_launches": int(launches.value) * steps, "e2e": e2e, "roofline": roofline, "cpu_baseline": cpu,
