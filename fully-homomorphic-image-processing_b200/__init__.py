@@ -120,6 +120,7 @@ def lib():
         "fhe_upload_async": (i32, [vp, vp, vp, C.c_size_t]),
         "fhe_download_async": (i32, [vp, vp, vp, C.c_size_t]),
         "fhe_transfer_fence": (i32, [vp, u32]),
+        "fhe_upload_fence": (i32, [vp, u32]),
         "fhe_device_broadcast": (i32, [vp, vp, vp, u32, u64]),
         "fhe_add_plain_each": (i32, [vp, vp, u64, u32, u64p, u32]),
         "fhe_profile_begin": (i32, [vp]),
@@ -148,7 +149,7 @@ EXPORTED_SYMBOLS = (
     "fhe_ntt_forward", "fhe_ntt_inverse", "fhe_dct_plan_create", "fhe_dct_plan_destroy",
     "fhe_dct8x8_quantize", "fhe_dct8x8_quantize_host", "fhe_fill_uniform", "fhe_checksum",
     "fhe_launch_count", "fhe_set_dct_chunk_blocks", "fhe_set_stage_timing", "fhe_get_stage_times",
-    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_encrypt_transparent", "fhe_ntt_loge", "fhe_multiply", "fhe_square", "fhe_form_create", "fhe_form_destroy", "fhe_multiply_form", "fhe_profile_begin", "fhe_profile_end", "fhe_device_broadcast", "fhe_add_plain_each", "fhe_upload_async", "fhe_download_async", "fhe_transfer_fence", "fhe_resize_plan_create", "fhe_resize_plan_destroy", "fhe_cubic", "fhe_linear", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
+    "fhe_jpeg_plan_create", "fhe_jpeg_plan_destroy", "fhe_jpeg_rgb_tiles", "fhe_device_zero", "fhe_encrypt_transparent", "fhe_ntt_loge", "fhe_multiply", "fhe_square", "fhe_form_create", "fhe_form_destroy", "fhe_multiply_form", "fhe_profile_begin", "fhe_profile_end", "fhe_device_broadcast", "fhe_add_plain_each", "fhe_upload_async", "fhe_download_async", "fhe_transfer_fence", "fhe_upload_fence", "fhe_resize_plan_create", "fhe_resize_plan_destroy", "fhe_cubic", "fhe_linear", "fhe_evk_digits", "fhe_evk_create", "fhe_evk_destroy", "fhe_relinearize",
 )
 
 

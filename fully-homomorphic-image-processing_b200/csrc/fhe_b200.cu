@@ -488,9 +488,10 @@ struct fhe_ctx {
     cudaEvent_t ev_in[kSlots]{}, ev_comp[kSlots]{}, ev_out[kSlots]{};
     // fhe_upload_async / fhe_download_async / fhe_transfer_fence
     static constexpr int kDown = 8;
-    cudaEvent_t ev_mark = nullptr, ev_up = nullptr, ev_down[kDown]{};
+    cudaEvent_t ev_mark = nullptr, ev_up = nullptr, ev_down[kDown]{}, ev_upr[kDown]{};
     bool up_pending = false;
     uint64_t down_issued = 0, down_waited = 0;  // downloads issued / known complete
+    uint64_t up_issued = 0, up_waited = 0;      // uploads issued / known complete (fhe_upload_fence)
     unsigned long long *d_scratch = nullptr;
     // optional per-kernel timing of the DCT path
     bool stage_timing = false;
@@ -749,6 +750,7 @@ int fhe_ctx_create(uint32_t n, uint32_t k, const uint64_t *q, uint64_t t, int de
     CU_TRY(cudaEventCreateWithFlags(&c->ev_mark, cudaEventDisableTiming));
     CU_TRY(cudaEventCreateWithFlags(&c->ev_up, cudaEventDisableTiming));
     for (int i = 0; i < fhe_ctx::kDown; ++i) CU_TRY(cudaEventCreateWithFlags(&c->ev_down[i], cudaEventDisableTiming));
+    for (int i = 0; i < fhe_ctx::kDown; ++i) CU_TRY(cudaEventCreateWithFlags(&c->ev_upr[i], cudaEventDisableTiming));
     const size_t tbytes = (size_t)k * n * sizeof(W2);
     CU_TRY(cudaMalloc(&c->d_tw, tbytes));
     CU_TRY(cudaMalloc(&c->d_itw, tbytes));
@@ -785,8 +787,10 @@ void fhe_ctx_destroy(fhe_ctx *c)
     clear_stage_events(c);
     if (c->ev_mark) cudaEventDestroy(c->ev_mark);
     if (c->ev_up) cudaEventDestroy(c->ev_up);
-    for (int i = 0; i < fhe_ctx::kDown; ++i)
+    for (int i = 0; i < fhe_ctx::kDown; ++i) {
         if (c->ev_down[i]) cudaEventDestroy(c->ev_down[i]);
+        if (c->ev_upr[i]) cudaEventDestroy(c->ev_upr[i]);
+    }
     for (auto &m : c->prof_marks) cudaEventDestroy(m.second);
     for (auto &kv : c->alloc_size) cudaFreeAsync(kv.first, c->stream);  // parked and still-live blocks alike
     cudaStreamSynchronize(c->stream);
@@ -979,15 +983,31 @@ static int wait_downloads(fhe_ctx *c, uint64_t keep)
     }
     return FHE_OK;
 }
+static int wait_uploads(fhe_ctx *c, uint64_t keep)
+{
+    while (c->up_waited + keep < c->up_issued) {
+        CU_TRY(cudaEventSynchronize(c->ev_upr[c->up_waited % fhe_ctx::kDown]));
+        ++c->up_waited;
+    }
+    return FHE_OK;
+}
+int fhe_upload_fence(fhe_ctx *c, uint32_t keep_uploads)
+{
+    if (int rc = check_ctx(c)) return rc;
+    return wait_uploads(c, keep_uploads);
+}
 int fhe_upload_async(fhe_ctx *c, void *d_dst, const void *h_src, size_t bytes)
 {
     if (int rc = check_ctx(c)) return rc;
     if (!d_dst || !h_src) return fail(FHE_ERR_INVALID_ARGUMENT, "null buffer");
+    if (int rc = wait_uploads(c, fhe_ctx::kDown - 1)) return rc;  // the event about to be reused has completed
     CU_TRY(cudaEventRecord(c->ev_mark, c->stream));
     CU_TRY(cudaStreamWaitEvent(c->s_in, c->ev_mark, 0));
     CU_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c->s_in));
     CU_TRY(cudaEventRecord(c->ev_up, c->s_in));
     c->up_pending = true;
+    CU_TRY(cudaEventRecord(c->ev_upr[c->up_issued % fhe_ctx::kDown], c->s_in));
+    ++c->up_issued;
     return FHE_OK;
 }
 int fhe_download_async(fhe_ctx *c, void *h_dst, const void *d_src, size_t bytes)

@@ -11,9 +11,10 @@
 //   the calls they replace (the colour conversion is the epilogue of the forward transform).
 //
 // Unlike the reference (one tile at a time, one Evaluator call at a time, "three blocks to not get
-// OOM", :109-111) tiles are streamed through the device in chunks: load a chunk from the file,
-// ONE fhe_jpeg_rgb_tiles call (forward NTT + colour conversion, pointwise DCT per channel, inverse
-// NTT), write the chunk back.  The server never loads the secret key (the reference does, "FOR
+// OOM", :109-111) tiles are streamed through the device in chunks, as a pipeline (stream_b200.hpp): a reader
+// thread parses the next chunk of the file, ONE fhe_jpeg_rgb_tiles call per chunk (forward NTT + colour
+// conversion, pointwise DCT per channel, inverse NTT) with the neighbouring chunks' copies beside it, a
+// writer thread serialises the results.  The server never loads the secret key (the reference does, "FOR
 // DEBUGGING ONLY", :97-98) and needs no public key on this path.
 // Extra flags: --quantize (also apply quantize_fhe with the JPEG luminance / chrominance tables,
 // fhe_image.h:99-100,294-305 -- the reference's main never calls it), --chunk N (tiles per call).
@@ -21,12 +22,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <fstream>
 #include <iostream>
 #include <string>
 
 #include "../host/fhe_image_b200.hpp"
 #include "../host/seal_wire_b200.hpp"
+#include "stream_b200.hpp"
 
 using namespace seal_b200;
 
@@ -122,23 +125,49 @@ int main(int argc, const char **argv)
             return 1;
         }
         const size_t W = context.ct_words(2), tile_words = 192 * W;
-        void *hbuf = nullptr, *dbuf = nullptr;
-        check(fhe_host_alloc((size_t)chunk_tiles * tile_words * 8, &hbuf));
-        check(fhe_device_alloc(context.handle(), (size_t)chunk_tiles * tile_words * 8, &dbuf));
-        uint64_t *h = (uint64_t *)hbuf;
-        std::vector<uint64_t> one;
-        WireHeader hdr;
-        check(fhe_set_stage_timing(context.handle(), 0));
-        for (int t0 = 0; t0 < num_blocks; t0 += chunk_tiles) {
-            const int nt = std::min(chunk_tiles, num_blocks - t0);
+        const size_t chunk_bytes = (size_t)chunk_tiles * tile_words * 8;
+        // Pipeline over chunks of tiles (stream_b200.hpp): the reader thread parses chunk c + 1 into pinned memory
+        // while chunk c is on the device and the writer thread serialises chunk c - 2; on the device, the upload of
+        // chunk c + 1 and the download of chunk c - 1 run beside the kernels of chunk c (three device buffers).
+        hash_block_type hash{};
+        stream_b200::Reader reader(3, (size_t)chunk_tiles * tile_words, [&](long u, stream_b200::Slot &slot) {
+            const long t0 = u * (long)chunk_tiles;
+            if (t0 >= num_blocks) return false;
+            const int nt = (int)std::min<long>(chunk_tiles, num_blocks - t0);
+            std::vector<uint64_t> one;
+            WireHeader hdr;
             for (size_t i = 0; i < (size_t)nt * 192; ++i) {
                 if (!load_ciphertext(myfile, context, one, hdr) || hdr.size != 2) throw std::invalid_argument("ciphertext stream ended early");
-                std::memcpy(h + i * W, one.data(), W * 8);
+                std::memcpy(slot.host + i * W, one.data(), W * 8);
             }
+            if (u == 0) hash = hdr.hash;  // published to the main thread with the slot (queue mutex)
+            slot.count = (size_t)nt;
+            return true;
+        });
+        stream_b200::Writer writer(3, (size_t)chunk_tiles * tile_words, [&](stream_b200::Slot &slot) {
+            for (size_t i = 0; i < slot.count * 192; ++i) save_ciphertext(outfile, context, slot.host + i * W, 2, hash);
+        });
+        void *dbuf[3] = {nullptr, nullptr, nullptr};
+        for (auto &d : dbuf) check(fhe_device_alloc(context.handle(), chunk_bytes, &d));
+        check(fhe_set_stage_timing(context.handle(), 0));
+        std::deque<stream_b200::Slot *> landing;  // output buffers whose downloads are in flight, oldest first
+        stream_b200::Slot *cur = reader.next();
+        if (cur) check(fhe_upload_async(context.handle(), dbuf[0], cur->host, cur->count * tile_words * 8));
+        for (long c = 0; cur; ++c) {
+            const int nt = (int)cur->count;
             const auto s0 = std::chrono::steady_clock::now();
-            check(fhe_upload(context.handle(), dbuf, h, (size_t)nt * tile_words * 8));
+            // the stream waits for the upload of chunk c; every download but the newest has landed
+            check(fhe_transfer_fence(context.handle(), 1));
+            while (landing.size() > 1) {
+                writer.submit(landing.front());
+                landing.pop_front();
+            }
+            stream_b200::Slot *nxt = reader.next();  // upload of chunk c + 1 beside the kernels of chunk c; its buffer
+            if (nxt)                                 // held chunk c - 2, whose download has landed
+                check(fhe_upload_async(context.handle(), dbuf[(c + 1) % 3], nxt->host, nxt->count * tile_words * 8));
+            void *d = dbuf[c % 3];
             check(fhe_profile_begin(context.handle()));
-            check(fhe_jpeg_rgb_tiles(context.handle(), plan, (const uint64_t *)dbuf, (uint64_t *)dbuf, (uint64_t)nt));
+            check(fhe_jpeg_rgb_tiles(context.handle(), plan, (const uint64_t *)d, (uint64_t *)d, (uint64_t)nt));
             // CSV contract (benchmark/analyze.py: per-label mean of the values): MEASURED device times of this
             // chunk's kernels -- RGBYCC: the colour-conversion pass per pixel; DCT: forward transforms +
             // pointwise DCT (+quantize) + inverse transforms per channel block (the transforms serve both
@@ -147,7 +176,8 @@ int main(int argc, const char **argv)
             float kms[16];
             uint64_t kcount[16];
             uint32_t nk = 0;
-            check(fhe_profile_end(context.handle(), names, sizeof names, kms, kcount, 16, &nk));
+            check(fhe_profile_end(context.handle(), names, sizeof names, kms, kcount, 16, &nk));  // the chunk's kernels are done
+            reader.recycle(cur);  // and with them the upload they waited for
             double color_ms = 0, dct_ms = 0;
             {
                 const char *p = names;
@@ -158,7 +188,10 @@ int main(int argc, const char **argv)
                     p = e ? e + 1 : p + name.size();
                 }
             }
-            check(fhe_download(context.handle(), h, dbuf, (size_t)nt * tile_words * 8));
+            stream_b200::Slot *o = writer.acquire();
+            o->count = (size_t)nt;
+            check(fhe_download_async(context.handle(), o->host, d, (size_t)nt * tile_words * 8));
+            landing.push_back(o);
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count();
             for (int t = 0; t < nt; ++t) {
                 std::cout << "RGBYCC,";
@@ -167,11 +200,13 @@ int main(int argc, const char **argv)
                 for (int i = 0; i < 3; ++i) std::cout << dct_ms / (3.0 * nt) << ',';
                 std::cout << std::endl;
             }
-            for (size_t i = 0; i < (size_t)nt * 192; ++i) save_ciphertext(outfile, context, h + i * W, 2, hdr.hash);
-            if (verbose) std::fprintf(stderr, "tiles %d..%d: %.3f ms\n", t0, t0 + nt - 1, ms);
+            if (verbose) std::fprintf(stderr, "tiles %ld..%ld: %.3f ms\n", c * chunk_tiles, c * chunk_tiles + nt - 1, ms);
+            cur = nxt;
         }
-        fhe_device_free(context.handle(), dbuf);
-        fhe_host_free(hbuf);
+        check(fhe_transfer_fence(context.handle(), 0));
+        for (stream_b200::Slot *o : landing) writer.submit(o);
+        writer.finish();
+        for (auto &d : dbuf) fhe_device_free(context.handle(), d);
         fhe_jpeg_plan_destroy(plan);
         return 0;
     } catch (const std::exception &e) {

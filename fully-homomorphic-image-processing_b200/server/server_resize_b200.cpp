@@ -16,18 +16,21 @@
 // tests compare both with the oracle).  The public fractions are encrypted with the key-less
 // transparent Encryptor: this server loads neither the public key nor the secret key the reference
 // reads "FOR DEBUGGING ONLY" (server_resize.cpp:99-116).
-// stdout: the label, then ONE measured value per output row -- the row's device + stream time in ms
+// stdout: the label, then ONE measured value per output row -- the pipeline's period for the row in ms
 // divided by the Cubic / Linear calls the reference would have made for it (15 / 9 per pixel), repeated
 // once per such call so that benchmark/analyze.py's per-label mean stays a per-call time.  The values
 // are row averages, not individual call timings (the calls of a row run as five fused launches).
 #include <chrono>
 #include <cstdio>
+#include <cstring>
+#include <deque>
 #include <fstream>
 #include <sstream>
 
 #include "../host/fhe_resize_b200.hpp"
 #include "../host/seal_wire_b200.hpp"
 #include "cli_b200.hpp"
+#include "stream_b200.hpp"
 
 using namespace seal_b200;
 
@@ -72,15 +75,47 @@ int main(int argc, const char **argv)
             std::fprintf(stderr, "server_resize_b200: cannot open %s or %s\n", ctext_infile.c_str(), ctext_outfile.c_str());
             return 1;
         }
-        WireHeader hdr;
-        std::vector<uint64_t> host;
-        RowSource source = [&](int, bool needed) {
-            CiphertextBatch row;
-            if (needed) row = CiphertextBatch(context, (size_t)original_width * 3, 2);
+        // Pipeline over rows (stream_b200.hpp): a reader thread parses the next source rows of the file into pinned
+        // memory, the row engine uploads them one output row ahead of the kernels (fhe_upload_async), output rows
+        // come back asynchronously (fhe_download_async) and a writer thread serialises them.
+        const size_t W2 = context.ct_words(2), in_row_words = (size_t)original_width * 3 * W2;
+        const uint32_t out_size = bicubic ? 6 : 4;
+        const size_t out_row_words = (size_t)resized_width * 3 * context.ct_words(out_size);
+        hash_block_type hash{};
+        stream_b200::Reader reader(6, in_row_words, [&](long y, stream_b200::Slot &slot) {
+            if (y >= original_height) return false;
+            std::vector<uint64_t> one;
+            WireHeader hdr;
             for (int i = 0; i < original_width * 3; ++i) {
-                if (!load_ciphertext(infile, context, host, hdr)) throw std::invalid_argument("ciphertext stream ended early");
+                if (!load_ciphertext(infile, context, one, hdr)) throw std::invalid_argument("ciphertext stream ended early");
                 if (hdr.size != 2) throw std::invalid_argument("input ciphertexts must have size 2");
-                if (needed) check(fhe_upload(context.handle(), row.element((size_t)i), host.data(), host.size() * sizeof(uint64_t)));
+                std::memcpy(slot.host + (size_t)i * W2, one.data(), W2 * sizeof(uint64_t));
+            }
+            if (y == 0) hash = hdr.hash;
+            slot.count = (size_t)original_width * 3;
+            return true;
+        });
+        stream_b200::Writer writer(3, out_row_words, [&](stream_b200::Slot &slot) {
+            const size_t w = context.ct_words(slot.size);
+            for (size_t i = 0; i < slot.count; ++i) save_ciphertext(outfile, context, slot.host + i * w, slot.size, hash);
+        });
+        std::deque<stream_b200::Slot *> uploading, landing;  // pinned buffers with a transfer in flight, oldest first
+        RowSource source = [&](int y, bool needed) {
+            stream_b200::Slot *s = reader.next();
+            if (!s || s->unit != y) throw std::invalid_argument("ciphertext stream ended early");
+            CiphertextBatch row;
+            if (!needed) {
+                reader.recycle(s);
+                return row;
+            }
+            row = CiphertextBatch(context, (size_t)original_width * 3, 2);
+            check(fhe_upload_async(context.handle(), row.device_data(), s->host, in_row_words * sizeof(uint64_t)));
+            uploading.push_back(s);
+            // at most four uploads in flight (two output rows' worth): older buffers go back to the reader
+            check(fhe_upload_fence(context.handle(), 4));
+            while (uploading.size() > 4) {
+                reader.recycle(uploading.front());
+                uploading.pop_front();
             }
             return row;
         };
@@ -89,17 +124,25 @@ int main(int argc, const char **argv)
         const size_t calls_per_row = (size_t)resized_width * (bicubic ? 15 : 9);
         RowResizer resizer(evaluator, encoder, encryptor, original_width, original_height, resized_width, resized_height, inter);
         auto t0 = std::chrono::steady_clock::now();
-        std::vector<uint64_t> out;
         resizer.run(source, [&](int, CiphertextBatch &row) {
-            context.sync();
+            // the engine has just waited for every download but the newest (fhe_transfer_fence(ctx, 1)): the host
+            // runs at most two rows ahead of the device, so the time between two calls is the pipeline's period
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            for (size_t i = 0; i < calls_per_row; ++i) std::cout << ms / calls_per_row << ',';
-            out.resize(context.ct_words(row.size()) * row.count());
-            row.download(out.data());
-            for (size_t i = 0; i < row.count(); ++i)
-                save_ciphertext(outfile, context, out.data() + i * context.ct_words(row.size()), row.size(), hdr.hash);
             t0 = std::chrono::steady_clock::now();
+            for (size_t i = 0; i < calls_per_row; ++i) std::cout << ms / calls_per_row << ',';
+            while (landing.size() > 1) {
+                writer.submit(landing.front());
+                landing.pop_front();
+            }
+            if (row.size() != out_size) throw std::logic_error("unexpected output ciphertext size");
+            stream_b200::Slot *o = writer.acquire();
+            o->count = row.count();
+            o->size = row.size();
+            check(fhe_download_async(context.handle(), o->host, row.device_data(), out_row_words * sizeof(uint64_t)));
+            landing.push_back(o);
         });
+        for (stream_b200::Slot *o : landing) writer.submit(o);  // run() returned after the last download landed
+        writer.finish();
         std::cout << std::endl;
         return 0;
     } catch (const std::exception &e) {

@@ -208,10 +208,14 @@ int fhe_multiply_form(fhe_ctx *ctx, const fhe_form *a, uint32_t a_div, const fhe
  * fhe_transfer_fence: (uploads) the context's stream waits for every upload issued so far -- call it
  * before the first kernel that reads an uploaded buffer; (downloads) the HOST waits until all downloads
  * except the keep_downloads most recent ones have landed -- call it before the source of an older
- * download is freed or overwritten, and with 0 before reading the last results on the host. */
+ * download is freed or overwritten, and with 0 before reading the last results on the host.
+ * fhe_upload_fence: the HOST waits until all uploads except the keep_uploads most recent ones have
+ * completed -- call it before the pinned source of an older upload is refilled (a reader thread that
+ * parses the next chunk of a ciphertext stream into a ring of pinned buffers, server/stream_b200.hpp). */
 int fhe_upload_async(fhe_ctx *ctx, void *d_dst, const void *h_src, size_t bytes);
 int fhe_download_async(fhe_ctx *ctx, void *h_dst, const void *d_src, size_t bytes);
 int fhe_transfer_fence(fhe_ctx *ctx, uint32_t keep_downloads);
+int fhe_upload_fence(fhe_ctx *ctx, uint32_t keep_uploads);
 
 /* count copies of one ciphertext (size polynomials) into consecutive elements of d_dst */
 int fhe_device_broadcast(fhe_ctx *ctx, uint64_t *d_dst, const uint64_t *d_src, uint32_t size, uint64_t count);

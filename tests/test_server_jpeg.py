@@ -24,9 +24,10 @@ def build_exe(pkg):
     pkg.build()
     libdir = os.path.join(ROOT, PKG_NAME)
     deps = [SRC, os.path.join(ROOT, "include", "fhe_b200.h")] + [
-        os.path.join(libdir, "host", f) for f in ("seal_b200.hpp", "fhe_image_b200.hpp", "seal_wire_b200.hpp")]
+        os.path.join(libdir, "host", f) for f in ("seal_b200.hpp", "fhe_image_b200.hpp", "seal_wire_b200.hpp")] + [
+        os.path.join(libdir, "server", "stream_b200.hpp")]
     if not os.path.exists(EXE) or any(os.path.getmtime(d) > os.path.getmtime(EXE) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-o", EXE, SRC, "-L" + libdir,
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-pthread", "-o", EXE, SRC, "-L" + libdir,
                                "-lfhe_b200", "-Wl,-rpath," + libdir])
     return EXE
 

@@ -19,10 +19,11 @@ LIBDIR = os.path.join(ROOT, PKG_NAME)
 def build(pkg, name, headers):
     pkg.build()
     src, exe = os.path.join(LIBDIR, "server", name + ".cpp"), os.path.join(LIBDIR, "server", name)
-    deps = [src, os.path.join(ROOT, "include", "fhe_b200.h"), os.path.join(LIBDIR, "server", "cli_b200.hpp")] + [
+    deps = [src, os.path.join(ROOT, "include", "fhe_b200.h"), os.path.join(LIBDIR, "server", "cli_b200.hpp"),
+            os.path.join(LIBDIR, "server", "stream_b200.hpp")] + [
         os.path.join(LIBDIR, "host", h) for h in headers]
     if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-o", exe, src, "-L" + LIBDIR,
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-pthread", "-o", exe, src, "-L" + LIBDIR,
                                "-lfhe_b200", "-Wl,-rpath," + LIBDIR])
     return exe
 
