@@ -19,6 +19,7 @@
 #pragma once
 #include <array>
 #include <cstdint>
+#include <cstring>
 #include <istream>
 #include <ostream>
 #include <stdexcept>
@@ -79,6 +80,62 @@ inline void save_ciphertext(std::ostream &out, const Context &ctx, const uint64_
         out.write((const char *)&zero, sizeof(zero));
     }
     if (!out) throw std::runtime_error("ciphertext stream: write failed");
+}
+
+// The same conversions on records held in memory (server/stream_b200.hpp reads and writes fixed-size records of a
+// stream with several threads: pread / pwrite at computed offsets).
+// bytes of a record that stores `capacity` polynomials
+inline size_t record_bytes(const Context &ctx, uint32_t capacity)
+{
+    return 4 * sizeof(uint64_t) + 4 * sizeof(int32_t) + (size_t)capacity * ctx.coeff_mod_count() * (ctx.poly_degree() + 1) * sizeof(uint64_t);
+}
+// header of a record (the first 48 bytes); throws like load_ciphertext on a mismatch with the context
+inline WireHeader parse_record_header(const unsigned char *rec, const Context &ctx)
+{
+    WireHeader hdr;
+    std::memcpy(hdr.hash.data(), rec, 32);
+    int32_t meta[4];
+    std::memcpy(meta, rec + 32, sizeof(meta));
+    hdr.size_capacity = meta[0];
+    hdr.size = meta[1];
+    hdr.poly_coeff_count = meta[2];
+    hdr.coeff_mod_count = meta[3];
+    if (hdr.size < 2 || hdr.size > hdr.size_capacity || hdr.poly_coeff_count != (int32_t)ctx.poly_degree() + 1 ||
+        hdr.coeff_mod_count != (int32_t)ctx.coeff_mod_count())
+        throw std::invalid_argument("ciphertext is not valid for encryption parameters");
+    return hdr;
+}
+// rec: a whole record of record_bytes(ctx, capacity) bytes; dst receives size * k * n words in device layout
+inline WireHeader parse_record(const unsigned char *rec, const Context &ctx, uint64_t *dst)
+{
+    const WireHeader hdr = parse_record_header(rec, ctx);
+    const uint32_t n = ctx.poly_degree(), k = ctx.coeff_mod_count();
+    const unsigned char *p = rec + 48;
+    for (size_t l = 0; l < (size_t)hdr.size * k; ++l, p += (size_t)(n + 1) * sizeof(uint64_t)) {
+        uint64_t *d = dst + l * n;
+        std::memcpy(d, p, (size_t)n * sizeof(uint64_t));
+        uint64_t pad;
+        std::memcpy(&pad, p + (size_t)n * sizeof(uint64_t), sizeof(pad));
+        const uint64_t q = ctx.coeff_modulus()[l % k];
+        uint64_t bad = pad;
+        for (uint32_t i = 0; i < n; ++i) bad |= (uint64_t)(d[i] >= q);
+        if (bad) throw std::invalid_argument(pad ? "ciphertext stream: non-zero padding coefficient" : "ciphertext coefficient is not reduced");
+    }
+    return hdr;
+}
+// rec: record_bytes(ctx, size) bytes
+inline void format_record(unsigned char *rec, const Context &ctx, const uint64_t *host, uint32_t size, const hash_block_type &hash)
+{
+    const uint32_t n = ctx.poly_degree(), k = ctx.coeff_mod_count();
+    std::memcpy(rec, hash.data(), 32);
+    const int32_t meta[4] = {(int32_t)size, (int32_t)size, (int32_t)n + 1, (int32_t)k};
+    std::memcpy(rec + 32, meta, sizeof(meta));
+    unsigned char *p = rec + 48;
+    const uint64_t zero = 0;
+    for (size_t l = 0; l < (size_t)size * k; ++l, p += (size_t)(n + 1) * sizeof(uint64_t)) {
+        std::memcpy(p, host + l * n, (size_t)n * sizeof(uint64_t));
+        std::memcpy(p + (size_t)n * sizeof(uint64_t), &zero, sizeof(zero));
+    }
 }
 
 // Ciphertext-level convenience (one H2D / D2H per record)

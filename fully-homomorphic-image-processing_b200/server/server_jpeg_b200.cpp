@@ -118,9 +118,11 @@ int main(int argc, const char **argv)
                                    quantize ? qy.data() : nullptr, quantize ? qc.data() : nullptr, &plan));
 
         const int num_blocks = WIDTH * HEIGHT / 64;  // server_jpeg.cpp:102 (tiles: R, G and B block each)
-        std::ifstream myfile(ctext_infile.c_str(), std::ios::binary);
-        std::ofstream outfile(ctext_outfile.c_str(), std::ios::binary);
-        if (!myfile || !outfile) {
+        struct Fd {
+            int fd;
+            ~Fd() { if (fd >= 0) ::close(fd); }
+        } myfile{::open(ctext_infile.c_str(), O_RDONLY)}, outfile{::open(ctext_outfile.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644)};
+        if (myfile.fd < 0 || outfile.fd < 0) {
             std::fprintf(stderr, "server_jpeg_b200: cannot open %s or %s\n", ctext_infile.c_str(), ctext_outfile.c_str());
             return 1;
         }
@@ -129,23 +131,40 @@ int main(int argc, const char **argv)
         // Pipeline over chunks of tiles (stream_b200.hpp): the reader thread parses chunk c + 1 into pinned memory
         // while chunk c is on the device and the writer thread serialises chunk c - 2; on the device, the upload of
         // chunk c + 1 and the download of chunk c - 1 run beside the kernels of chunk c (three device buffers).
-        hash_block_type hash{};
+        // The records of a stream have one size (the client writes them with one set of parameters): the first header
+        // gives it, and the helper threads read / write record i at i * record size, several at a time.
+        unsigned char head[48];
+        if (!stream_b200::pread_exact(myfile.fd, head, sizeof head, 0)) throw std::invalid_argument("ciphertext stream ended early");
+        const WireHeader first = parse_record_header(head, context);
+        if (first.size != 2) throw std::invalid_argument("input ciphertexts must have size 2");
+        const hash_block_type hash = first.hash;
+        const size_t in_rec = record_bytes(context, (uint32_t)first.size_capacity), out_rec = record_bytes(context, 2);
+        const unsigned io = stream_b200::io_threads();
         stream_b200::Reader reader(3, (size_t)chunk_tiles * tile_words, [&](long u, stream_b200::Slot &slot) {
             const long t0 = u * (long)chunk_tiles;
             if (t0 >= num_blocks) return false;
             const int nt = (int)std::min<long>(chunk_tiles, num_blocks - t0);
-            std::vector<uint64_t> one;
-            WireHeader hdr;
-            for (size_t i = 0; i < (size_t)nt * 192; ++i) {
-                if (!load_ciphertext(myfile, context, one, hdr) || hdr.size != 2) throw std::invalid_argument("ciphertext stream ended early");
-                std::memcpy(slot.host + i * W, one.data(), W * 8);
-            }
-            if (u == 0) hash = hdr.hash;  // published to the main thread with the slot (queue mutex)
+            stream_b200::parallel_ranges((size_t)nt * 192, io, [&](size_t b, size_t e) {
+                std::vector<unsigned char> rec(in_rec);
+                for (size_t i = b; i < e; ++i) {
+                    if (!stream_b200::pread_exact(myfile.fd, rec.data(), in_rec, ((uint64_t)t0 * 192 + i) * in_rec))
+                        throw std::invalid_argument("ciphertext stream ended early");
+                    const WireHeader hdr = parse_record(rec.data(), context, slot.host + i * W);
+                    if (hdr.size != 2 || hdr.size_capacity != first.size_capacity)
+                        throw std::invalid_argument("ciphertext stream: records of different sizes");
+                }
+            });
             slot.count = (size_t)nt;
             return true;
         });
         stream_b200::Writer writer(3, (size_t)chunk_tiles * tile_words, [&](stream_b200::Slot &slot) {
-            for (size_t i = 0; i < slot.count * 192; ++i) save_ciphertext(outfile, context, slot.host + i * W, 2, hash);
+            stream_b200::parallel_ranges(slot.count * 192, io, [&](size_t b, size_t e) {
+                std::vector<unsigned char> rec(out_rec);
+                for (size_t i = b; i < e; ++i) {
+                    format_record(rec.data(), context, slot.host + i * W, 2, hash);
+                    stream_b200::pwrite_exact(outfile.fd, rec.data(), out_rec, ((uint64_t)slot.unit * chunk_tiles * 192 + i) * out_rec);
+                }
+            });
         });
         void *dbuf[3] = {nullptr, nullptr, nullptr};
         for (auto &d : dbuf) check(fhe_device_alloc(context.handle(), chunk_bytes, &d));
@@ -190,6 +209,7 @@ int main(int argc, const char **argv)
             }
             stream_b200::Slot *o = writer.acquire();
             o->count = (size_t)nt;
+            o->unit = c;
             check(fhe_download_async(context.handle(), o->host, d, (size_t)nt * tile_words * 8));
             landing.push_back(o);
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - s0).count();

@@ -69,9 +69,11 @@ int main(int argc, const char **argv)
         Evaluator evaluator(context);
         FractionalEncoder encoder(context, (uint32_t)opt.num("ncoeff", 100), (uint32_t)opt.num("fcoeff", 100), 2);
         Encryptor encryptor(context);
-        std::ifstream infile(ctext_infile.c_str(), std::ios::binary);
-        std::ofstream outfile(ctext_outfile.c_str(), std::ios::binary);
-        if (!infile || !outfile) {
+        struct Fd {
+            int fd;
+            ~Fd() { if (fd >= 0) ::close(fd); }
+        } infile{::open(ctext_infile.c_str(), O_RDONLY)}, outfile{::open(ctext_outfile.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0644)};
+        if (infile.fd < 0 || outfile.fd < 0) {
             std::fprintf(stderr, "server_resize_b200: cannot open %s or %s\n", ctext_infile.c_str(), ctext_outfile.c_str());
             return 1;
         }
@@ -81,23 +83,38 @@ int main(int argc, const char **argv)
         const size_t W2 = context.ct_words(2), in_row_words = (size_t)original_width * 3 * W2;
         const uint32_t out_size = bicubic ? 6 : 4;
         const size_t out_row_words = (size_t)resized_width * 3 * context.ct_words(out_size);
-        hash_block_type hash{};
+        // records of one size: record i of the stream sits at i * record size; the helper threads read / write several at a time
+        unsigned char head[48];
+        if (!stream_b200::pread_exact(infile.fd, head, sizeof head, 0)) throw std::invalid_argument("ciphertext stream ended early");
+        const WireHeader first = parse_record_header(head, context);
+        if (first.size != 2) throw std::invalid_argument("input ciphertexts must have size 2");
+        const hash_block_type hash = first.hash;
+        const size_t in_rec = record_bytes(context, (uint32_t)first.size_capacity), out_rec = record_bytes(context, out_size);
+        const size_t in_per_row = (size_t)original_width * 3, out_per_row = (size_t)resized_width * 3, Wout = context.ct_words(out_size);
+        const unsigned io = stream_b200::io_threads();
         stream_b200::Reader reader(6, in_row_words, [&](long y, stream_b200::Slot &slot) {
             if (y >= original_height) return false;
-            std::vector<uint64_t> one;
-            WireHeader hdr;
-            for (int i = 0; i < original_width * 3; ++i) {
-                if (!load_ciphertext(infile, context, one, hdr)) throw std::invalid_argument("ciphertext stream ended early");
-                if (hdr.size != 2) throw std::invalid_argument("input ciphertexts must have size 2");
-                std::memcpy(slot.host + (size_t)i * W2, one.data(), W2 * sizeof(uint64_t));
-            }
-            if (y == 0) hash = hdr.hash;
-            slot.count = (size_t)original_width * 3;
+            stream_b200::parallel_ranges(in_per_row, io, [&](size_t b, size_t e) {
+                std::vector<unsigned char> rec(in_rec);
+                for (size_t i = b; i < e; ++i) {
+                    if (!stream_b200::pread_exact(infile.fd, rec.data(), in_rec, ((uint64_t)y * in_per_row + i) * in_rec))
+                        throw std::invalid_argument("ciphertext stream ended early");
+                    const WireHeader hdr = parse_record(rec.data(), context, slot.host + i * W2);
+                    if (hdr.size != 2 || hdr.size_capacity != first.size_capacity)
+                        throw std::invalid_argument("ciphertext stream: records of different sizes");
+                }
+            });
+            slot.count = in_per_row;
             return true;
         });
         stream_b200::Writer writer(3, out_row_words, [&](stream_b200::Slot &slot) {
-            const size_t w = context.ct_words(slot.size);
-            for (size_t i = 0; i < slot.count; ++i) save_ciphertext(outfile, context, slot.host + i * w, slot.size, hash);
+            stream_b200::parallel_ranges(slot.count, io, [&](size_t b, size_t e) {
+                std::vector<unsigned char> rec(out_rec);
+                for (size_t i = b; i < e; ++i) {
+                    format_record(rec.data(), context, slot.host + i * Wout, out_size, hash);
+                    stream_b200::pwrite_exact(outfile.fd, rec.data(), out_rec, ((uint64_t)slot.unit * out_per_row + i) * out_rec);
+                }
+            });
         });
         std::deque<stream_b200::Slot *> uploading, landing;  // pinned buffers with a transfer in flight, oldest first
         RowSource source = [&](int y, bool needed) {
@@ -124,7 +141,7 @@ int main(int argc, const char **argv)
         const size_t calls_per_row = (size_t)resized_width * (bicubic ? 15 : 9);
         RowResizer resizer(evaluator, encoder, encryptor, original_width, original_height, resized_width, resized_height, inter);
         auto t0 = std::chrono::steady_clock::now();
-        resizer.run(source, [&](int, CiphertextBatch &row) {
+        resizer.run(source, [&](int y, CiphertextBatch &row) {
             // the engine has just waited for every download but the newest (fhe_transfer_fence(ctx, 1)): the host
             // runs at most two rows ahead of the device, so the time between two calls is the pipeline's period
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -138,6 +155,7 @@ int main(int argc, const char **argv)
             stream_b200::Slot *o = writer.acquire();
             o->count = row.count();
             o->size = row.size();
+            o->unit = y;
             check(fhe_download_async(context.handle(), o->host, row.device_data(), out_row_words * sizeof(uint64_t)));
             landing.push_back(o);
         });
