@@ -40,7 +40,7 @@ def emu_lib():
     d = os.path.join(ROOT, "tests", "emu")
     so, src = os.path.join(d, "libfhe_emu.so"), os.path.join(d, "emu.cpp")
     csrc = os.path.join(ROOT, PKG_NAME, "csrc")
-    deps = [src] + [os.path.join(csrc, f) for f in ("ntt.cuh", "dct.cuh", "modarith.cuh", "ring_host.hpp",
+    deps = [src] + [os.path.join(csrc, f) for f in ("ntt.cuh", "ntt_generic.cuh", "dct.cuh", "modarith.cuh", "ring_host.hpp",
                                                       "behz.cuh", "behz_host.hpp")]
     if not os.path.exists(so) or any(os.path.getmtime(x) > os.path.getmtime(so) for x in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", so, src])
