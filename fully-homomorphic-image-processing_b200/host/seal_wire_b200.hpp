@@ -31,6 +31,17 @@ namespace seal_b200 {
 
 using hash_block_type = std::array<uint64_t, 4>;
 
+// Header variant.  The layout above is recalled, not checked against a file written by SEAL (absent here); the
+// field most likely to differ between 2.3.x releases is size_capacity.  wire_has_capacity() = false selects
+// records WITHOUT it (hash block, then size, poly_coeff_count, coeff_mod_count: 44 header bytes, data of
+// exactly `size` polynomials); the servers expose it as `--wire nocapacity`.  Process-wide, set before any I/O.
+inline bool &wire_has_capacity()
+{
+    static bool v = true;
+    return v;
+}
+inline size_t wire_header_bytes() { return 4 * sizeof(uint64_t) + (wire_has_capacity() ? 4 : 3) * sizeof(int32_t); }
+
 struct WireHeader {
     hash_block_type hash{};
     int32_t size_capacity = 0, size = 0, poly_coeff_count = 0, coeff_mod_count = 0;
@@ -43,8 +54,10 @@ inline bool load_ciphertext(std::istream &in, const Context &ctx, std::vector<ui
     in.read((char *)hdr.hash.data(), sizeof(uint64_t) * 4);
     if (in.gcount() == 0 && in.eof()) return false;
     int32_t meta[4];
-    in.read((char *)meta, sizeof(meta));
+    const bool cap = wire_has_capacity();
+    in.read((char *)(meta + (cap ? 0 : 1)), (cap ? 4 : 3) * sizeof(int32_t));
     if (!in) throw std::invalid_argument("ciphertext stream: truncated header");
+    if (!cap) meta[0] = meta[1];
     hdr.size_capacity = meta[0];
     hdr.size = meta[1];
     hdr.poly_coeff_count = meta[2];
@@ -73,7 +86,8 @@ inline void save_ciphertext(std::ostream &out, const Context &ctx, const uint64_
     const uint32_t n = ctx.poly_degree(), k = ctx.coeff_mod_count();
     out.write((const char *)hash.data(), sizeof(uint64_t) * 4);
     const int32_t meta[4] = {(int32_t)size, (int32_t)size, (int32_t)n + 1, (int32_t)k};
-    out.write((const char *)meta, sizeof(meta));
+    const bool cap = wire_has_capacity();
+    out.write((const char *)(meta + (cap ? 0 : 1)), (cap ? 4 : 3) * sizeof(int32_t));
     const uint64_t zero = 0;
     for (size_t p = 0; p < (size_t)size * k; ++p) {
         out.write((const char *)(host + p * n), (std::streamsize)(n * sizeof(uint64_t)));
@@ -87,15 +101,17 @@ inline void save_ciphertext(std::ostream &out, const Context &ctx, const uint64_
 // bytes of a record that stores `capacity` polynomials
 inline size_t record_bytes(const Context &ctx, uint32_t capacity)
 {
-    return 4 * sizeof(uint64_t) + 4 * sizeof(int32_t) + (size_t)capacity * ctx.coeff_mod_count() * (ctx.poly_degree() + 1) * sizeof(uint64_t);
+    return wire_header_bytes() + (size_t)capacity * ctx.coeff_mod_count() * (ctx.poly_degree() + 1) * sizeof(uint64_t);
 }
-// header of a record (the first 48 bytes); throws like load_ciphertext on a mismatch with the context
+// header of a record (its first wire_header_bytes() bytes); throws like load_ciphertext on a mismatch with the context
 inline WireHeader parse_record_header(const unsigned char *rec, const Context &ctx)
 {
     WireHeader hdr;
     std::memcpy(hdr.hash.data(), rec, 32);
     int32_t meta[4];
-    std::memcpy(meta, rec + 32, sizeof(meta));
+    const bool cap = wire_has_capacity();
+    std::memcpy(meta + (cap ? 0 : 1), rec + 32, (cap ? 4 : 3) * sizeof(int32_t));
+    if (!cap) meta[0] = meta[1];
     hdr.size_capacity = meta[0];
     hdr.size = meta[1];
     hdr.poly_coeff_count = meta[2];
@@ -110,7 +126,7 @@ inline WireHeader parse_record(const unsigned char *rec, const Context &ctx, uin
 {
     const WireHeader hdr = parse_record_header(rec, ctx);
     const uint32_t n = ctx.poly_degree(), k = ctx.coeff_mod_count();
-    const unsigned char *p = rec + 48;
+    const unsigned char *p = rec + wire_header_bytes();
     for (size_t l = 0; l < (size_t)hdr.size * k; ++l, p += (size_t)(n + 1) * sizeof(uint64_t)) {
         uint64_t *d = dst + l * n;
         std::memcpy(d, p, (size_t)n * sizeof(uint64_t));
@@ -129,8 +145,9 @@ inline void format_record(unsigned char *rec, const Context &ctx, const uint64_t
     const uint32_t n = ctx.poly_degree(), k = ctx.coeff_mod_count();
     std::memcpy(rec, hash.data(), 32);
     const int32_t meta[4] = {(int32_t)size, (int32_t)size, (int32_t)n + 1, (int32_t)k};
-    std::memcpy(rec + 32, meta, sizeof(meta));
-    unsigned char *p = rec + 48;
+    const bool cap = wire_has_capacity();
+    std::memcpy(rec + 32, meta + (cap ? 0 : 1), (cap ? 4 : 3) * sizeof(int32_t));
+    unsigned char *p = rec + wire_header_bytes();
     const uint64_t zero = 0;
     for (size_t l = 0; l < (size_t)size * k; ++l, p += (size_t)(n + 1) * sizeof(uint64_t)) {
         std::memcpy(p, host + l * n, (size_t)n * sizeof(uint64_t));

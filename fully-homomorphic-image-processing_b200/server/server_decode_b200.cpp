@@ -26,12 +26,20 @@ int main(int argc, const char **argv)
 {
     cli_b200::Spec spec;
     spec.alias = {{"-f", "file"}, {"-o", "outfile"}, {"-v", "verbose"}};
-    spec.valued = {"file", "outfile", "delta", "order", "degree", "ncoeff", "fcoeff", "cmod", "pmod", "base"};
+    spec.valued = {"file", "outfile", "delta", "order", "degree", "ncoeff", "fcoeff", "cmod", "pmod", "base", "wire"};
     spec.switches = {"verbose", "help"};
     const cli_b200::Parsed opt = cli_b200::parse(argc, argv, spec);
+    if (opt.has("wire")) {  // header variant of the ciphertext records (host/seal_wire_b200.hpp)
+        const std::string v = opt.str("wire", "capacity");
+        if (v != "capacity" && v != "nocapacity") {
+            std::cout << "error parsing options: --wire takes capacity or nocapacity" << std::endl;
+            return 1;
+        }
+        wire_has_capacity() = v == "capacity";
+    }
     if (opt.has("help")) {
         std::printf("%s [-f in] [-o out] [--delta d] [--order o] [--degree g] [--ncoeff N] [--fcoeff N] [--cmod n] [--pmod t] "
-                    "[--base b] [-v]\n  ciphertext stream layout: host/seal_wire_b200.hpp (SEAL 2.3 layout from recall, UNVERIFIED against real SEAL files)\n", argv[0]);
+                    "[--base b] [-v]\n  ciphertext stream layout: host/seal_wire_b200.hpp (SEAL 2.3 layout from recall, UNVERIFIED against real SEAL files);\n  --wire nocapacity: records whose header has no size_capacity field\n", argv[0]);
         return 0;
     }
     int pairs[3] = {0, 0, 0}, width = 0, height = 0;

@@ -44,8 +44,9 @@ static const double kColor[9] = {0.299, 0.587, 0.114, -0.168736, 0.331264, 0.5, 
 static void usage(const char *argv0)
 {
     std::printf("%s [-f|--file in] [-o|--outfile out] [--ncoeff N] [--fcoeff N] [--cmod n] [--pmod t] [--base b]\n"
-                "        [--quantize] [--chunk tiles] [-v|--verbose] [--help]\n"
-                "  ciphertext stream layout: host/seal_wire_b200.hpp (SEAL 2.3 layout from recall, UNVERIFIED against real SEAL files)\n", argv0);
+                "        [--quantize] [--chunk tiles] [--wire capacity|nocapacity] [-v|--verbose] [--help]\n"
+                "  ciphertext stream layout: host/seal_wire_b200.hpp (SEAL 2.3 layout from recall, UNVERIFIED against real SEAL files);\n"
+                "  --wire nocapacity reads and writes records whose header has no size_capacity field\n", argv0);
 }
 
 int main(int argc, const char **argv)
@@ -74,6 +75,14 @@ int main(int argc, const char **argv)
         else if (a == "--base") n_poly_base = std::atoi(val("base").c_str());
         else if (a == "--quantize") quantize = true;
         else if (a == "--chunk") chunk_tiles = std::atoi(val("chunk").c_str());
+        else if (a == "--wire") {
+            const std::string v = val("wire");
+            if (v != "capacity" && v != "nocapacity") {
+                std::cout << "error parsing options: --wire takes capacity or nocapacity" << std::endl;
+                return 1;
+            }
+            wire_has_capacity() = v == "capacity";
+        }
         else if (a == "--help") {
             usage(argv[0]);
             return 0;
@@ -134,7 +143,7 @@ int main(int argc, const char **argv)
         // The records of a stream have one size (the client writes them with one set of parameters): the first header
         // gives it, and the helper threads read / write record i at i * record size, several at a time.
         unsigned char head[48];
-        if (!stream_b200::pread_exact(myfile.fd, head, sizeof head, 0)) throw std::invalid_argument("ciphertext stream ended early");
+        if (!stream_b200::pread_exact(myfile.fd, head, wire_header_bytes(), 0)) throw std::invalid_argument("ciphertext stream ended early");
         const WireHeader first = parse_record_header(head, context);
         if (first.size != 2) throw std::invalid_argument("input ciphertexts must have size 2");
         const hash_block_type hash = first.hash;

@@ -38,12 +38,20 @@ int main(int argc, const char **argv)
 {
     cli_b200::Spec spec;
     spec.alias = {{"-f", "file"}, {"-o", "outfile"}, {"-v", "verbose"}, {"-w", "width"}, {"-h", "height"}};
-    spec.valued = {"file", "outfile", "ncoeff", "fcoeff", "cmod", "pmod", "width", "height", "base"};
+    spec.valued = {"file", "outfile", "ncoeff", "fcoeff", "cmod", "pmod", "width", "height", "base", "wire"};
     spec.switches = {"bicubic", "verbose", "help"};
     const cli_b200::Parsed opt = cli_b200::parse(argc, argv, spec);
+    if (opt.has("wire")) {  // header variant of the ciphertext records (host/seal_wire_b200.hpp)
+        const std::string v = opt.str("wire", "capacity");
+        if (v != "capacity" && v != "nocapacity") {
+            std::cout << "error parsing options: --wire takes capacity or nocapacity" << std::endl;
+            return 1;
+        }
+        wire_has_capacity() = v == "capacity";
+    }
     if (opt.has("help")) {
         std::printf("%s [-f in] [-o out] [--bicubic] -w W -h H [--ncoeff N] [--fcoeff N] [--cmod n] [--pmod t] [--base b] "
-                    "[-v]\n  ciphertext stream layout: host/seal_wire_b200.hpp (SEAL 2.3 layout from recall, UNVERIFIED against real SEAL files)\n", argv[0]);
+                    "[-v]\n  ciphertext stream layout: host/seal_wire_b200.hpp (SEAL 2.3 layout from recall, UNVERIFIED against real SEAL files);\n  --wire nocapacity: records whose header has no size_capacity field\n", argv[0]);
         return 0;
     }
     int original_width = 0, original_height = 0, channels = 0;
@@ -85,7 +93,7 @@ int main(int argc, const char **argv)
         const size_t out_row_words = (size_t)resized_width * 3 * context.ct_words(out_size);
         // records of one size: record i of the stream sits at i * record size; the helper threads read / write several at a time
         unsigned char head[48];
-        if (!stream_b200::pread_exact(infile.fd, head, sizeof head, 0)) throw std::invalid_argument("ciphertext stream ended early");
+        if (!stream_b200::pread_exact(infile.fd, head, wire_header_bytes(), 0)) throw std::invalid_argument("ciphertext stream ended early");
         const WireHeader first = parse_record_header(head, context);
         if (first.size != 2) throw std::invalid_argument("input ciphertexts must have size 2");
         const hash_block_type hash = first.hash;

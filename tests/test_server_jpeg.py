@@ -147,6 +147,53 @@ def test_server_jpeg_end_to_end_on_gpu(pkg, oracle_mod, tmp_path):
 
 
 @pytest.mark.gpu
+def test_wire_header_variant_without_size_capacity(pkg, oracle_mod, tmp_path):
+    """the record layout is recalled, not checked against SEAL; the field most likely to differ is
+    size_capacity.  `--wire nocapacity` reads and writes records without it: same ciphertexts, 4 bytes less each."""
+    exe = build_exe(pkg)
+    n, width, height = 2048, 8, 8           # one tile
+    q = oracle_mod.default_coeff_modulus(n)
+    o = oracle_mod.Oracle(n, q, 1 << 14)
+    k = o.k
+    rng = np.random.default_rng(11)
+    cts = [rng.integers(0, min(q), size=2 * k * n, dtype=np.uint64) for _ in range(192)]
+    outs = {}
+    for variant in ("capacity", "nocapacity"):
+        d = tmp_path / variant
+        os.makedirs(d / "keys")
+        os.makedirs(d / "image")
+        (d / "keys" / "params.txt").write_text(f"{width} {height} 3 {1 << 14}\n")
+        with open(d / "image" / "nothingpersonnel.txt", "wb") as f:
+            for ct in cts:
+                f.write(struct.pack("<4Q", *HASH))
+                f.write(struct.pack("<4i", 2, 2, n + 1, k) if variant == "capacity" else struct.pack("<3i", 2, n + 1, k))
+                rows = np.zeros((2 * k, n + 1), dtype="<u8")
+                rows[:, :n] = ct.reshape(2 * k, n)
+                f.write(rows.tobytes())
+        r = subprocess.run([exe, "--cmod", str(n), "--pmod", str(1 << 14), "--wire", variant], capture_output=True, text=True,
+                           cwd=d, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        raw = (d / "image" / "zoop.txt").read_bytes()
+        head = 32 + (16 if variant == "capacity" else 12)
+        rec = head + 2 * k * (n + 1) * 8
+        assert len(raw) == 192 * rec
+        recs = []
+        for i in range(192):
+            b = raw[i * rec:(i + 1) * rec]
+            assert struct.unpack("<4Q", b[:32]) == HASH
+            meta = struct.unpack("<4i" if variant == "capacity" else "<3i", b[32:head])
+            assert meta == ((2, 2, n + 1, k) if variant == "capacity" else (2, n + 1, k))
+            recs.append(np.frombuffer(b[head:], dtype="<u8").reshape(2 * k, n + 1))
+        outs[variant] = recs
+    for a, b in zip(outs["capacity"], outs["nocapacity"]):
+        assert (a == b).all()
+    # a stream of the other variant is refused, not mis-parsed
+    r = subprocess.run([exe, "--cmod", str(n), "--pmod", str(1 << 14), "--wire", "nocapacity"], capture_output=True, text=True,
+                       cwd=tmp_path / "capacity", timeout=600)
+    assert r.returncode != 0
+
+
+@pytest.mark.gpu
 def test_published_rms_error_through_the_encrypted_pipeline(pkg, oracle_mod, tmp_path):
     """image/boazbarak.jpg (48 x 48, committed fixture) -> client-side encryption of every pixel
     (oracle harness) -> server_jpeg_b200 on the GPU -> decryption -> this repo's JPEG writer ->
