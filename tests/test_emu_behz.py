@@ -1,6 +1,6 @@
-"""CPU execution of the BEHZ kernel bodies (csrc/behz.cuh, ntt_wide.cuh via tests/emu/emu.cpp) against
-the oracle: base extension, the 61-bit Harvey NTT over B_sk, tensor, scaling -- and the whole multiply
-sequenced as the library does it.  Checks the merged constants (m~^-1, t, q^-1, B^-1 folded into the
+"""CPU execution of the BEHZ kernel bodies (csrc/behz.cuh via tests/emu/emu.cpp) against
+the oracle: base extension into the library's 55-bit auxiliary base, the transforms over B_sk, tensor, scaling
+(fold_aux / reduce_u128 routes included) -- and the whole multiply sequenced as the library does it.  Checks the merged constants (m~^-1, t, q^-1, B^-1 folded into the
 conversion matrices) and the table conventions with no GPU."""
 import ctypes as C
 
