@@ -18,6 +18,7 @@
 #include <functional>
 #include <mutex>
 #include <stdexcept>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -78,7 +79,12 @@ protected:
     {
         for (Slot &s : slots_) {
             void *p = nullptr;
-            if (fhe_host_alloc(words * sizeof(uint64_t), &p) != FHE_OK) throw std::runtime_error(fhe_last_error());
+            if (fhe_host_alloc(words * sizeof(uint64_t), &p) != FHE_OK) {
+                const std::string why = fhe_last_error();
+                for (Slot &t : slots_)  // the destructor does not run for a half-built ring
+                    if (t.host) fhe_host_free(t.host);
+                throw std::runtime_error(why);
+            }
             s.host = (uint64_t *)p;
             s.words = words;
             free_.push(&s);
