@@ -11,6 +11,7 @@
 // A pinned buffer returns to its ring when the transfer that used it has completed (fhe_upload_fence /
 // fhe_transfer_fence on the main thread).  Errors on a helper thread are rethrown on the main thread.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
@@ -121,7 +122,7 @@ public:
             try {
                 for (long u = 0;; ++u) {
                     Slot *s = free_.pop();
-                    if (!s) break;
+                    if (!s || stop_) break;
                     s->unit = u;
                     if (!fill(u, *s)) break;
                     ready_.push(s);
@@ -134,6 +135,7 @@ public:
     }
     ~Reader()
     {
+        stop_ = true;  // do not parse further units into the buffers that are still free
         free_.close();
         if (th_.joinable()) th_.join();
     }
@@ -146,6 +148,9 @@ public:
     }
     // the upload that read `s` has completed
     void recycle(Slot *s) { free_.push(s); }
+
+private:
+    std::atomic<bool> stop_{false};
 };
 
 // drain(slot) serialises one unit; units are drained in the order they are submitted
